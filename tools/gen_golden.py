@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.json from the LIVE reference (development container only).
+
+Imports the unmodified reference from /root/reference (pure-Python path), first
+runs the reference's own TestFields known-answer tests, then records inputs and
+outputs for every hot-path function.  The reference cannot travel to the GPU
+box, these fixtures can.  Usage:  python tools/gen_golden.py
+
+Encoding: a field element of level L (1, 2, 6, 12) is the hex of its
+``serialize()`` bytes, 48 bytes big-endian per coefficient in ZT order.
+"""
+import json
+import logging
+import os
+import random
+import sys
+import unittest
+
+logging.disable(logging.CRITICAL)
+sys.dont_write_bytecode = True
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, os.path.join(ROOT, "python-bls_b200"))
+
+from bls_py import tdata, tests as ref_tests            # noqa: E402
+from bls_py import ec as rec, pairing as rpair          # noqa: E402
+from bls_py.aggregation_info import AggregationInfo     # noqa: E402
+from bls_py.bls import BLS                              # noqa: E402
+from bls_py.fields import Fq, Fq2, Fq6, Fq12            # noqa: E402
+from bls_py.keys import PrivateKey, PublicKey           # noqa: E402
+from bls_py.signature import Signature                  # noqa: E402
+from bls_py.util import hash256                         # noqa: E402
+from bls_b200 import synth                              # noqa: E402
+
+Q = rec.default_ec.q
+N = rec.default_ec.n
+OUT = os.path.join(ROOT, "tests", "golden")
+CLS = {1: Fq, 2: Fq2, 6: Fq6, 12: Fq12}
+
+
+def flat(e):
+    return (e.Z,) if isinstance(e, Fq) else tuple(e.ZT)
+
+
+def hx(e):
+    return b"".join(c.to_bytes(48, "big") for c in flat(e)).hex()
+
+
+def lift(e, level):
+    """embed a lower-level element at coefficient 0, as the mixed-type operators do"""
+    f = flat(e)
+    f = f + (0,) * (level - len(f))
+    return Fq(Q, f[0]) if level == 1 else CLS[level](Q, f)
+
+
+def dump(name, obj):
+    path = os.path.join(OUT, name)
+    with open(path, "w") as fh:
+        json.dump(obj, fh, indent=0, separators=(",", ":"))
+        fh.write("\n")
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+# ---------------------------------------------------------------------------
+def field_kat():
+    """Replays the operation sweep of tests.py:434-1036 on tdata's operands and
+    checks that EVERY expected value in tdata's result lists is reproduced."""
+    suite = unittest.defaultTestLoader.loadTestsFromTestCase(ref_tests.TestFields)
+    res = unittest.TextTestRunner(verbosity=0, stream=open(os.devnull, "w")).run(suite)
+    assert res.wasSuccessful(), "reference TestFields failed"
+
+    ops = {"add": lambda a, b: a + b, "mul": lambda a, b: a * b,
+           "sub": lambda a, b: a - b}
+    lists = {1: tdata.fq_list, 2: tdata.fq2_list, 6: tdata.fq6_list, 12: tdata.fq12_list}
+    expected = {1: tdata.fq_res_list, 2: tdata.fq2_res_list,
+                6: tdata.fq6_res_list, 12: tdata.fq12_res_list}
+    cases = []
+    for level in (1, 2, 6, 12):
+        seen = set()
+        for la in (1, 2, 6, 12):
+            for lb in (1, 2, 6, 12):
+                if max(la, lb) != level:
+                    continue
+                for i in range(4):
+                    for j in range(i + 1, 4):
+                        a, b = lists[la][i], lists[lb][j]
+                        for name, fn in ops.items():
+                            out = fn(a, b)
+                            assert type(out) is CLS[level]
+                            seen.add(flat(out))
+                            # operands are tdata operand i of level la / j of level lb,
+                            # embedded at coefficient 0 of `level`
+                            cases.append({"level": level, "op": name, "a": [la, i],
+                                          "b": [lb, j], "out": hx(out)})
+        for i in range(4):
+            a = lists[level][i]
+            for name, out in (("neg", -a), ("inv", ~a), ("sqr", a * a)):
+                seen.add(flat(out))
+                cases.append({"level": level, "op": name, "a": [level, i], "out": hx(out)})
+        missing = [k for k, e in enumerate(expected[level][:-1]) if flat(e) not in seen]
+        assert not missing, (level, missing)
+    # Frobenius (tests.py:60-68) and powers on seeded random elements
+    rnd = random.Random(0xF0B)
+    for level in (2, 6, 12):
+        a = CLS[level](Q, tuple(rnd.randrange(Q) for _ in range(level)))
+        for i in range(level):
+            out = a.qi_power(i)
+            if level == 2 or i in (1, 2, 3, 6):
+                assert out == pow(a, pow(Q, i))
+            cases.append({"level": level, "op": "frob", "a": hx(a), "i": i, "out": hx(out)})
+        e = rnd.getrandbits(300)
+        cases.append({"level": level, "op": "pow", "a": hx(a), "e": hex(e), "out": hx(a ** e)})
+    # square roots (fields.py:199-205, 463-482)
+    for _ in range(6):
+        a = Fq(Q, rnd.randrange(Q))
+        cases.append({"level": 1, "op": "sqrt", "a": hx(a * a), "out": hx((a * a).modsqrt())})
+        b = Fq2(Q, rnd.randrange(Q), rnd.randrange(Q))
+        cases.append({"level": 2, "op": "sqrt", "a": hx(b * b), "out": hx((b * b).modsqrt())})
+    n_fail = 0
+    while n_fail < 4:
+        b = Fq2(Q, rnd.randrange(Q), rnd.randrange(Q))
+        try:
+            b.modsqrt()
+        except ValueError:
+            n_fail += 1
+            cases.append({"level": 2, "op": "sqrt", "a": hx(b), "out": None})
+    operands = {str(lv): [hx(e) for e in lists[lv]] for lv in (1, 2, 6, 12)}
+    dump("field_kat.json", {"source": "bls_py/tdata.py via tests.py:434-1036 + live reference",
+                            "operands": operands, "cases": cases})
+
+
+# ---------------------------------------------------------------------------
+def aff_g1(p):
+    return {"x": hx(p.x), "y": hx(p.y), "inf": bool(p.infinity)}
+
+
+aff_g2 = aff_g1
+
+
+def curve_kat():
+    g1, g2 = rec.generator_Fq(), rec.generator_Fq2()
+    ks = [1, 2, 3, 5, 0xd201000000010000, N - 1, N, N + 7, 0] + synth.scalar_ints(0xC0DE, 6)
+    out = {"g1_mul": [], "g2_mul": [], "g1_add": [], "g2_add": []}
+    pts1, pts2 = [], []
+    for k in ks:
+        p1 = (g1.to_jacobian() * k).to_affine()
+        p2 = (g2.to_jacobian() * k).to_affine()
+        pts1.append(p1)
+        pts2.append(p2)
+        out["g1_mul"].append({"k": hex(k), "p": aff_g1(g1), "out": aff_g1(p1),
+                              "ser": p1.serialize().hex()})
+        out["g2_mul"].append({"k": hex(k), "p": aff_g2(g2), "out": aff_g2(p2),
+                              "ser": p2.serialize().hex()})
+    # k * (non-generator point)
+    for k in synth.scalar_ints(0xC0DF, 3):
+        out["g1_mul"].append({"k": hex(k), "p": aff_g1(pts1[-1]),
+                              "out": aff_g1((pts1[-1].to_jacobian() * k).to_affine())})
+        out["g2_mul"].append({"k": hex(k), "p": aff_g2(pts2[-1]),
+                              "out": aff_g2((pts2[-1].to_jacobian() * k).to_affine())})
+
+    def add_case(lst, a, b, key):
+        try:
+            s = (a.to_jacobian() + b.to_jacobian()).to_affine()
+            lst.append({"a": aff_g1(a), "b": aff_g1(b), "out": aff_g1(s), "ser": s.serialize().hex()})
+        except TypeError:
+            # fields_t.py:781: the pure-Python G1 P+P path raises; recorded as the
+            # mathematically correct doubling computed through scalar mult
+            s = (a.to_jacobian() * 2).to_affine()
+            lst.append({"a": aff_g1(a), "b": aff_g1(b), "out": aff_g1(s),
+                        "ser": s.serialize().hex(), "note": "reference raises TypeError (defect)"})
+
+    for pts, key in ((pts1, "g1_add"), (pts2, "g2_add")):
+        inf = pts[ks.index(N)]
+        assert inf.infinity
+        pairs = [(pts[0], pts[1]), (pts[2], pts[3]), (pts[9], pts[10]), (pts[11], pts[12]),
+                 (pts[3], pts[3]), (pts[0], pts[5]), (inf, pts[4]), (pts[4], inf), (inf, inf)]
+        for a, b in pairs:
+            add_case(out[key], a, b, key)
+    dump("curve_kat.json", out)
+
+
+# ---------------------------------------------------------------------------
+def pairing_kat():
+    g1, g2 = rec.generator_Fq(), rec.generator_Fq2()
+    sc = synth.scalar_ints(synth.SEED_PAIRING, 16)
+    cases = []
+    pairs = [(1, 1), (3, 7), (5, 11)] + [(sc[2 * i], sc[2 * i + 1]) for i in range(5)]
+    pts = []
+    for a, b in pairs:
+        p, q = (g1.to_jacobian() * a).to_affine(), (g2.to_jacobian() * b).to_affine()
+        pts.append((p, q))
+        e = rpair.ate_pairing(p, q)
+        cases.append({"a": hex(a), "b": hex(b), "p": aff_g1(p), "q": aff_g2(q), "out": hx(e)})
+    multi = []
+    for idx in ([1, 2], [0, 3, 4], [5]):
+        ps, qs = [pts[i][0] for i in idx], [pts[i][1] for i in idx]
+        multi.append({"idx": idx, "out": hx(rpair.ate_pairing_multi(ps, qs))})
+    # degenerate inputs: infinity flags are ignored by the reference Miller loop
+    zero1 = rec.AffinePoint(Fq(Q, 0), Fq(Q, 0), True, rec.default_ec)
+    zero2 = rec.AffinePoint(Fq2.zero(Q), Fq2.zero(Q), True, rec.default_ec_twist)
+    degenerate = [{"p": aff_g1(zero1), "q": aff_g2(g2), "out": hx(rpair.ate_pairing(zero1, g2))},
+                  {"p": aff_g1(g1), "q": aff_g2(zero2), "out": hx(rpair.ate_pairing(g1, zero2))}]
+    ml = rpair.miller_loop(g1, g2)
+    dump("pairing_kat.json", {"pairs": cases, "multi": multi, "degenerate": degenerate,
+                              "miller_loop_g1_g2": hx(ml),
+                              "final_exp_of_miller": hx(rpair.final_exponentiation(ml, rec.default_ec))})
+
+
+# ---------------------------------------------------------------------------
+def hash_kat():
+    cases = []
+    hs = [hash256(bytes([7, 8, 9])), hash256(b""), hash256(b"chia")]
+    hs += [bytes(r) for r in synth.message_hashes(0x4A54, 21)]
+    for h in hs:
+        p = rec.hash_to_point_prehashed_Fq2(h)
+        cases.append({"h": h.hex(), "out": aff_g2(p), "ser": p.serialize().hex()})
+    sw = []
+    rnd = random.Random(0x5E)
+    ts = [Fq2(Q, 0, 0), Fq2(Q, 1, 0), Fq2(Q, 0, 1), Fq2(Q, Q - 1, 0), Fq2(Q, 5, Q - 3)]
+    ts += [Fq2(Q, rnd.randrange(Q), rnd.randrange(Q)) for _ in range(24)]
+    for t in ts:
+        p = rec.sw_encode(t, rec.default_ec_twist, Fq2)
+        if isinstance(p, rec.JacobianPoint):
+            p = p.to_affine()
+        sw.append({"t": hx(t), "out": aff_g2(p)})
+    psi = []
+    g2 = rec.generator_Fq2()
+    for k in (1, 5):
+        p = (g2.to_jacobian() * k).to_affine()
+        psi.append({"p": aff_g2(p), "out": aff_g2(rec.psi(p, rec.default_ec))})
+    dump("hash_kat.json", {"hash_to_g2_prehashed": cases, "sw_encode": sw, "psi": psi})
+
+
+# ---------------------------------------------------------------------------
+def sig_kat():
+    """tests.py:113-198 vectors re-derived from the live reference, plus verify
+    truth tables and corrupted-signature behaviour."""
+    suite = unittest.TestSuite([ref_tests.TestBLS("test_vectors"), ref_tests.TestBLS("test_vectors2")])
+    res = unittest.TextTestRunner(verbosity=0, stream=open(os.devnull, "w")).run(suite)
+    assert res.wasSuccessful(), "reference test_vectors failed"
+
+    seeds = [bytes([1, 2, 3, 4, 5]), bytes([1, 2, 3, 4, 5, 6])]
+    sks = [PrivateKey.from_seed(s) for s in seeds]
+    pks = [sk.get_public_key() for sk in sks]
+    keys_out = [{"seed": s.hex(), "sk": sk.serialize().hex(), "pk": pk.serialize().hex(),
+                 "fingerprint": pk.get_fingerprint()} for s, sk, pk in zip(seeds, sks, pks)]
+    assert keys_out[0]["fingerprint"] == 0x26d53247 and keys_out[1]["fingerprint"] == 0x289bb56e
+
+    msgs = [bytes([7, 8, 9]), bytes([1, 2, 3]), bytes([1, 2, 3, 4]), bytes([1, 2]),
+            bytes([1, 2, 3, 40]), bytes([5, 6, 70, 201]), bytes([9, 10, 11, 12, 13]),
+            bytes([15, 63, 244, 92, 0, 1])]
+    signs = []
+    for ki, sk in enumerate(sks):
+        for m in msgs:
+            signs.append({"key": ki, "msg": m.hex(), "sig": sk.sign(m).serialize().hex()})
+
+    sig1, sig2 = sks[0].sign(msgs[0]), sks[1].sign(msgs[0])
+    agg_sig = BLS.aggregate_sigs([sig1, sig2])
+    agg_pk = BLS.aggregate_pub_keys([pks[0], pks[1]], True)
+    agg_pk_simple = BLS.aggregate_pub_keys([pks[0], pks[1]], False)
+    agg_sk = BLS.aggregate_priv_keys(sks, pks, True)
+    v = {"secure_agg_sig": agg_sig.serialize().hex(),
+         "secure_agg_pk": agg_pk.serialize().hex(),
+         "simple_agg_pk": agg_pk_simple.serialize().hex(),
+         "secure_agg_sk": agg_sk.serialize().hex(),
+         "verify_sig1": BLS.verify(sig1), "verify_agg": BLS.verify(agg_sig)}
+    agg_sig.set_aggregation_info(AggregationInfo.from_msg(agg_pk, msgs[0]))
+    v["verify_agg_with_agg_pk"] = BLS.verify(agg_sig)
+    sig1.set_aggregation_info(sig2.aggregation_info)
+    v["verify_sig1_wrong_info"] = BLS.verify(sig1)
+    sig3, sig4, sig5 = sks[0].sign(msgs[1]), sks[0].sign(msgs[2]), sks[1].sign(msgs[3])
+    agg2 = BLS.aggregate_sigs([sig3, sig4, sig5])
+    v["distinct_agg_sig"] = agg2.serialize().hex()
+    v["verify_distinct_agg"] = BLS.verify(agg2)
+
+    m1, m2, m3, m4 = msgs[4:8]
+    s1, s2, s3 = sks[0].sign(m1), sks[1].sign(m2), sks[1].sign(m1)
+    s4, s5, s6 = sks[0].sign(m3), sks[0].sign(m1), sks[0].sign(m4)
+    sig_l = BLS.aggregate_sigs([s1, s2])
+    sig_r = BLS.aggregate_sigs([s3, s4, s5])
+    sig_final = BLS.aggregate_sigs([sig_l, sig_r, s6])
+    v2 = {"sig_L": sig_l.serialize().hex(), "sig_R": sig_r.serialize().hex(),
+          "sig_final": sig_final.serialize().hex(),
+          "verify_L": BLS.verify(sig_l), "verify_R": BLS.verify(sig_r),
+          "verify_final": BLS.verify(sig_final),
+          "final_tree": sorted([[k[0].hex(), k[1].serialize().hex(), hex(e)]
+                                for k, e in sig_final.aggregation_info.tree.items()])}
+    quotient = sig_final.divide_by([s2, s5, s6])
+    v2["quotient"] = quotient.serialize().hex()
+    v2["verify_quotient"] = BLS.verify(quotient)
+
+    # single-signature verify truth table on raw (pk, message hash, sig) triples
+    table = []
+    for ki in (0, 1):
+        for m in msgs[:3]:
+            sig = sks[ki].sign(m)
+            h = hash256(m)
+            table.append({"pk": pks[ki].serialize().hex(), "h": h.hex(),
+                          "sig": sig.serialize().hex(), "ok": True})
+            table.append({"pk": pks[1 - ki].serialize().hex(), "h": h.hex(),
+                          "sig": sig.serialize().hex(), "ok": False})
+            table.append({"pk": pks[ki].serialize().hex(), "h": hash256(m + b"!").hex(),
+                          "sig": sig.serialize().hex(), "ok": False})
+    for t in table:      # confirm with the reference itself
+        try:
+            s = Signature.from_bytes(bytes.fromhex(t["sig"]))
+            s.set_aggregation_info(AggregationInfo.from_msg_hash(
+                PublicKey.from_bytes(bytes.fromhex(t["pk"])), bytes.fromhex(t["h"])))
+            got = BLS.verify(s)
+        except Exception:
+            got = False
+        assert got == t["ok"], t
+
+    # byte-level corruption of a valid signature (about half raise)
+    good = sks[0].sign(msgs[0])
+    raw = good.serialize()
+    flips = []
+    rnd = random.Random(0xBADF11)
+    for _ in range(24):
+        pos, bit = rnd.randrange(96), rnd.randrange(8)
+        if pos == 0 and bit >= 5:
+            bit = rnd.randrange(5)       # keep clear of the flag bits
+        bad = bytearray(raw)
+        bad[pos] ^= 1 << bit
+        entry = {"sig": bytes(bad).hex()}
+        try:
+            s = Signature.from_bytes(bytes(bad))
+            entry["decodes"] = True
+            entry["point"] = aff_g2(s.value.to_affine())
+            s.set_aggregation_info(good.aggregation_info)
+            entry["ok"] = BLS.verify(s)
+        except Exception:
+            entry["decodes"] = False
+            entry["ok"] = False
+        flips.append(entry)
+    dump("sig_kat.json", {"keys": keys_out, "sign": signs, "test_vectors": v,
+                          "test_vectors2": v2, "verify_table": table,
+                          "bitflips": {"pk": pks[0].serialize().hex(),
+                                       "h": hash256(msgs[0]).hex(), "cases": flips}})
+
+
+# ---------------------------------------------------------------------------
+def agg_kat():
+    """config-3 semantics (bls.py:13-26, 204-223 secure=False) at small N."""
+    g1, g2 = rec.generator_Fq().to_jacobian(), rec.generator_Fq2().to_jacobian()
+    ks = synth.scalar_ints(synth.SEED_AGGREGATE, 1000)
+    p1 = [(g1 * k) for k in ks]
+    p2 = [(g2 * k) for k in ks]
+    out = []
+    for n in (1, 2, 3, 1000):
+        s1, s2 = p1[0], p2[0]
+        for i in range(1, n):
+            s1 = s1 + p1[i]
+            s2 = s2 + p2[i]
+        assert s1.serialize() == (g1 * (sum(ks[:n]) % N)).serialize()
+        assert s2.serialize() == (g2 * (sum(ks[:n]) % N)).serialize()
+        out.append({"n": n, "seed": synth.SEED_AGGREGATE,
+                    "g1_sum": s1.serialize().hex(), "g2_sum": s2.serialize().hex()})
+    # secure public-key aggregation (bls.py:204-223 with T_i exponents), n = 4
+    pks = [PublicKey.from_g1(p) for p in p1[:4]]
+    sec = BLS.aggregate_pub_keys(list(pks), True)
+    dump("agg_kat.json", {"sums": out,
+                          "points_head": {"g1": [p.serialize().hex() for p in p1[:4]],
+                                          "g2": [p.serialize().hex() for p in p2[:4]]},
+                          "secure_pk_agg": {"pks": [p.serialize().hex() for p in pks],
+                                            "out": sec.serialize().hex()}})
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["field", "curve", "pairing", "hash", "sig", "agg"]
+    for w in which:
+        globals()[w + "_kat"]()
