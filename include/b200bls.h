@@ -1,0 +1,109 @@
+/* b200bls.h -- C ABI of libb200bls.so, the B200 (sm_100a) engine for python-bls's
+ * pairing / aggregation hot path.
+ *
+ * This is the drop-in boundary.  The reference's own plugin seam is the set
+ * of tuple-in / tuple-out functions that bls_py/fields_t.py:1218-1265 re-imports from the
+ * Cython module extmod/bls_py/fields_t_c.pyx -- one field operation, one point operation or
+ * one pairing per Python call.  A GPU needs batches, so every entry point here is the
+ * *batched, byte-buffer* form of one of those functions; the citation on each declaration
+ * names the reference function(s) it replaces (paths relative to /root/reference).
+ *
+ * Encoding = the reference's own serialize() bytes, so parity is a memcmp:
+ *   Fq      48 bytes big-endian                       (bls_py/fields.py:87-88)
+ *   Fq2/6/12  2/6/12 such coefficients in ZT order      (bls_py/fields.py:273-278)
+ *   G1 affine  x || y            =  96 bytes, point at infinity = all zero bytes
+ *   G2 affine  x.c0 x.c1 y.c0 y.c1 = 192 bytes, point at infinity = all zero bytes
+ *   G1 / G2 compressed 48 / 96 bytes                  (bls_py/ec.py:94-111)
+ *   scalars 32 bytes big-endian;  message hashes 32 bytes
+ * Inputs are reduced mod q on load exactly like Fq(Q, int) does (bls_py/fields.py:59-61).
+ *
+ * Conventions: every function returns 0 on success and a negative B200BLS_E_* code on
+ * failure (no exceptions cross the ABI; b200bls_last_error() describes the last failure of
+ * the calling thread).  The caller owns every buffer; the library keeps no pointer after a
+ * call returns.  Host-buffer entry points copy to the GPU, run, copy back and synchronise.
+ * The *_dev variants take device pointers obtained from b200bls_malloc() and only enqueue
+ * work on the library's stream (call b200bls_sync()).  One process drives one GPU
+ * (b200bls_init(device)); a global mutex serialises calls.  There is NO CPU fallback: without
+ * a CUDA device b200bls_init() fails and every compute call returns B200BLS_E_NOT_INIT.
+ */
+#ifndef B200BLS_H
+#define B200BLS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200BLS_OK 0
+#define B200BLS_E_NOT_INIT (-1)
+#define B200BLS_E_CUDA (-2)
+#define B200BLS_E_ARG (-3)
+#define B200BLS_E_NOMEM (-4)
+#define B200BLS_E_PROGRAM (-5)
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+int b200bls_init(int device);            /* select GPU `device`, upload the field programs */
+void b200bls_shutdown(void);
+const char* b200bls_last_error(void);
+int b200bls_sm_count(void);              /* SMs of the initialised device, 0 if none */
+int b200bls_sync(void);                  /* wait for the library stream */
+
+/* ---- device / pinned memory for resident-data pipelines and benchmarks ----------------- */
+void* b200bls_malloc(size_t bytes);
+void b200bls_free(void* dev_ptr);
+void* b200bls_host_alloc(size_t bytes);  /* pinned host memory */
+void b200bls_host_free(void* host_ptr);
+int b200bls_h2d(void* dev_dst, const void* host_src, size_t bytes);   /* async on the stream */
+int b200bls_d2h(void* host_dst, const void* dev_src, size_t bytes);   /* async on the stream */
+/* CUDA-event timing on the library stream: tic, enqueue work, toc -> milliseconds */
+int b200bls_timer_start(void);
+int b200bls_timer_stop(float* ms_out);
+/* kernels launched by this library since init (bench.py's gpu_launches) */
+uint64_t b200bls_launch_count(void);
+
+/* Integer-multiply roofline microbenchmark.  variant 0: IMAD (mad.lo),
+ * 1: IMAD.HI, 2: IMAD.WIDE.U32, 3: IMAD.WIDE.U32.X carry chains as in the Montgomery
+ * product.  Launches blocks_per_sm x SMs CTAs of `threads` threads (<= 256); reports
+ * multiply-add instructions per second (best of 4 timed launches, CUDA events). */
+int b200bls_microbench_imad(int variant, int blocks_per_sm, int threads, int iters,
+                            double* ops_per_second, float* ms_out);
+
+/* ---- generic program launch (device pointers) ------------------------------------------ */
+/* Runs the embedded field program `name` over n_items; bufs[i] / strides[i] (bytes per item)
+ * are the program's numbered byte buffers.  Typed entry points below are thin wrappers. */
+int b200bls_run_program_dev(const char* name, size_t n_items, void* const* bufs,
+                            const int64_t* strides, int n_bufs);
+int b200bls_program_info(const char* name, int* n_ins, int* n_slots, int* n_cold);
+
+/* ---- field tower: level in {1, 2, 6, 12} coefficients -------------------------------------
+ * op: 0 add, 1 sub, 2 mul, 3 sqr, 4 neg, 5 inv.  a, b, out: n x (48 * level) bytes.
+ * Replaces the fq_ / fq2_ / fq6_ / fq12_ functions of bls_py/fields_t.py:47-554
+ * (add, sub, neg, mul, invert)
+ * and the operator methods of Fq/Fq2/Fq6/Fq12 (bls_py/fields.py:35-764). b is ignored for
+ * unary ops.  Inverse of 0 is 0 as in fq_invert (fields_t.py:47-55). */
+int b200bls_field_op_batch(int level, int op, const uint8_t* a, const uint8_t* b,
+                           uint8_t* out, size_t n);
+int b200bls_field_op_batch_dev(int level, int op, const void* a, const void* b, void* out,
+                               size_t n);
+
+/* ---- pairing ------------------------------------------------------------------------------
+ * P: n x 96 (G1 affine), Q: n x 192 (G2 affine). */
+/* fq_miller_loop + fq12_final_exp per pair (fields_t.py:1091-1128; pairing.py:76-81
+ * ate_pairing).  out: n x 576. */
+int b200bls_pairing_batch(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n);
+int b200bls_pairing_batch_dev(const void* P, const void* Q, void* out, size_t n);
+/* fq12_final_exp (fields_t.py:1124-1128; pairing.py:68-73).  in/out: n x 576. */
+int b200bls_final_exp_batch(const uint8_t* in, uint8_t* out, size_t n);
+int b200bls_final_exp_batch_dev(const void* in, void* out, size_t n);
+/* Miller loop alone.  NOT byte-comparable with fq_miller_loop (fields_t.py:1091-1111): the
+ * value differs from the reference's by a factor that the final exponentiation removes
+ * (projective, denominator-free lines).  final_exp(out) is canonical. out: n x 576. */
+int b200bls_miller_loop_batch(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n);
+int b200bls_miller_loop_batch_dev(const void* P, const void* Q, void* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BLS_H */

@@ -1,0 +1,122 @@
+"""Batched byte-buffer operations on the GPU (thin, typed layer over the C ABI).
+
+All inputs/outputs are numpy uint8 arrays (or bytes) in the reference's serialisation
+(48-byte big-endian coefficients).  This is the layer the bls_py-compatible classes and
+bench.py call; it owns no arithmetic.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_u8, check, lib, ptr
+
+FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "neg": 4, "inv": 5}
+
+
+def field_op(level, op, a, b=None):
+    """n elements of tower level 1/2/6/12 -> n results; a, b: n * 48 * level bytes"""
+    _lib.init()
+    a = as_u8(a)
+    w = 48 * level
+    n = a.size // w
+    if a.size != n * w:
+        raise ValueError("operand size is not a multiple of %d" % w)
+    opc = FIELD_OPS[op]
+    bb = as_u8(b, a.size) if opc <= 2 else None
+    out = np.empty(n * w, dtype=np.uint8)
+    check(lib.b200bls_field_op_batch(level, opc, ptr(a), ptr(bb) if bb is not None else None, ptr(out), n))
+    return out
+
+
+def _pq(P, Q):
+    P, Q = as_u8(P), as_u8(Q)
+    n = P.size // 96
+    if P.size != n * 96 or Q.size != n * 192:
+        raise ValueError("P must be n*96 bytes and Q n*192 bytes")
+    return P, Q, n
+
+
+def pairing_batch(P, Q):
+    """n independent ate pairings -> n * 576 bytes (bls_py.pairing.ate_pairing per pair)"""
+    _lib.init()
+    P, Q, n = _pq(P, Q)
+    out = np.empty(n * 576, dtype=np.uint8)
+    check(lib.b200bls_pairing_batch(ptr(P), ptr(Q), ptr(out), n))
+    return out
+
+
+def miller_loop_batch(P, Q):
+    _lib.init()
+    P, Q, n = _pq(P, Q)
+    out = np.empty(n * 576, dtype=np.uint8)
+    check(lib.b200bls_miller_loop_batch(ptr(P), ptr(Q), ptr(out), n))
+    return out
+
+
+def final_exp_batch(f):
+    _lib.init()
+    f = as_u8(f)
+    n = f.size // 576
+    out = np.empty(n * 576, dtype=np.uint8)
+    check(lib.b200bls_final_exp_batch(ptr(f), ptr(out), n))
+    return out
+
+
+class DeviceBuffer:
+    """device memory owned by the library (for resident-data pipelines and benchmarks)"""
+
+    def __init__(self, nbytes):
+        _lib.init()
+        self.nbytes = nbytes
+        self.ptr = lib.b200bls_malloc(nbytes)
+        if not self.ptr:
+            raise _lib.B200BlsError(lib.b200bls_last_error().decode())
+
+    def upload(self, host):
+        host = as_u8(host)
+        assert host.size <= self.nbytes
+        check(lib.b200bls_h2d(self.ptr, ptr(host), host.size))
+        check(lib.b200bls_sync())
+        return self
+
+    def download(self, nbytes=None):
+        out = np.empty(nbytes or self.nbytes, dtype=np.uint8)
+        check(lib.b200bls_d2h(ptr(out), self.ptr, out.size))
+        check(lib.b200bls_sync())
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib.b200bls_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def run_program_dev(name, n_items, bufs, strides):
+    arr = (ctypes.c_void_p * len(bufs))(*[b.ptr if isinstance(b, DeviceBuffer) else b for b in bufs])
+    st = (ctypes.c_int64 * len(bufs))(*strides)
+    check(lib.b200bls_run_program_dev(name.encode(), n_items, arr, st, len(bufs)))
+
+
+def timer_start():
+    check(lib.b200bls_timer_start())
+
+
+def timer_stop():
+    ms = ctypes.c_float()
+    check(lib.b200bls_timer_stop(ctypes.byref(ms)))
+    return ms.value
+
+
+def microbench_imad(variant, blocks_per_sm=8, threads=256, iters=200):
+    _lib.init()
+    ops = ctypes.c_double()
+    ms = ctypes.c_float()
+    check(lib.b200bls_microbench_imad(variant, blocks_per_sm, threads, iters, ctypes.byref(ops), ctypes.byref(ms)))
+    return ops.value, ms.value

@@ -1,0 +1,243 @@
+"""Fq6 / Fq12 tower arithmetic expressed as VM programs over Fq2 values.
+
+Tower (same as the reference, bls_py/fields.py:322/486/625):
+  Fq6  = Fq2[v]/(v^3 - xi),  xi = 1 + u
+  Fq12 = Fq6[w]/(w^2 - v)
+The reference multiplies with hand-expanded schoolbook formulas (36 / 144 integer products,
+bls_py/fields_t.py:293-318, 503-554); here Karatsuba at every level (18 Fq2 products per
+Fq12 product) -- results are canonical field elements either way.
+"""
+from ..vm.builder import Q
+
+XI = (1, 1)
+
+
+def f2_pow_int(a, e):
+    """plain-int Fq2 power for constant generation"""
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = ((r[0] * a[0] - r[1] * a[1]) % Q, (r[0] * a[1] + r[1] * a[0]) % Q)
+        a = ((a[0] * a[0] - a[1] * a[1]) % Q, 2 * a[0] * a[1] % Q)
+        e >>= 1
+    return r
+
+
+def frob_gamma(i):
+    """gamma[k] = xi^(k (q^i - 1) / 6): (c w^k)^(q^i) = conj^i(c) gamma[k] w^k
+    (the values the reference tabulates at fields_t.py:1133-1216)"""
+    g = f2_pow_int(XI, (Q ** i - 1) // 6)
+    tab = [(1, 0)]
+    for _ in range(5):
+        t = tab[-1]
+        tab.append(((t[0] * g[0] - t[1] * g[1]) % Q, (t[0] * g[1] + t[1] * g[0]) % Q))
+    return tab
+
+
+class F6:
+    """a0 + a1 v + a2 v^2"""
+    __slots__ = ("a0", "a1", "a2")
+
+    def __init__(self, a0, a1, a2):
+        self.a0, self.a1, self.a2 = a0, a1, a2
+
+    def __add__(self, o):
+        return F6(self.a0 + o.a0, self.a1 + o.a1, self.a2 + o.a2)
+
+    def __sub__(self, o):
+        return F6(self.a0 - o.a0, self.a1 - o.a1, self.a2 - o.a2)
+
+    def __neg__(self):
+        return F6(-self.a0, -self.a1, -self.a2)
+
+    def dbl(self):
+        return F6(self.a0.dbl(), self.a1.dbl(), self.a2.dbl())
+
+    def mul_v(self):
+        return F6(self.a2.mul_xi(), self.a0, self.a1)
+
+    def __mul__(self, o):
+        a0, a1, a2, b0, b1, b2 = self.a0, self.a1, self.a2, o.a0, o.a1, o.a2
+        v0, v1, v2 = a0 * b0, a1 * b1, a2 * b2
+        c0 = v0 + ((a1 + a2) * (b1 + b2) - v1 - v2).mul_xi()
+        c1 = (a0 + a1) * (b0 + b1) - v0 - v1 + v2.mul_xi()
+        c2 = (a0 + a2) * (b0 + b2) - v0 - v2 + v1
+        return F6(c0, c1, c2)
+
+    def sqr(self):
+        a0, a1, a2 = self.a0, self.a1, self.a2
+        s0 = a0.sqr()
+        s1 = (a0 * a1).dbl()
+        s2 = (a0 - a1 + a2).sqr()
+        s3 = (a1 * a2).dbl()
+        s4 = a2.sqr()
+        return F6(s0 + s3.mul_xi(), s1 + s4.mul_xi(), s1 + s2 + s3 - s0 - s4)
+
+    def mul_by_01(self, c0, c1):
+        """times (c0 + c1 v)"""
+        a0, a1, a2 = self.a0, self.a1, self.a2
+        t0, t1 = a0 * c0, a1 * c1
+        r0 = t0 + (a2 * c1).mul_xi()
+        r1 = (a0 + a1) * (c0 + c1) - t0 - t1
+        r2 = t1 + a2 * c0
+        return F6(r0, r1, r2)
+
+    def mul_by_1(self, c1):
+        """times c1 v"""
+        return F6((self.a2 * c1).mul_xi(), self.a0 * c1, self.a1 * c1)
+
+    def mul_fp2(self, c):
+        return F6(self.a0 * c, self.a1 * c, self.a2 * c)
+
+    def inv(self, fp_inv):
+        """norm down to Fq2 (as bls_py/fields_t.py:170-184), one Fq inversion via fp_inv"""
+        a0, a1, a2 = self.a0, self.a1, self.a2
+        g0 = a0.sqr() - (a1 * a2).mul_xi()
+        g1 = a2.sqr().mul_xi() - a0 * a1
+        g2 = a1.sqr() - a0 * a2
+        n = a0 * g0 + (a2 * g1 + a1 * g2).mul_xi()
+        t = f2_inv(n, fp_inv)
+        return F6(g0 * t, g1 * t, g2 * t)
+
+
+def f2_inv(a, fp_inv):
+    """conj(a) / (c0^2 + c1^2)  (bls_py/fields_t.py:81-85)"""
+    n = a.c0.sqr() + a.c1.sqr()
+    t = fp_inv(n)
+    return a.conj() * t
+
+
+class F12:
+    """c0 + c1 w, c0, c1 in Fq6"""
+    __slots__ = ("c0", "c1")
+
+    def __init__(self, c0, c1):
+        self.c0, self.c1 = c0, c1
+
+    def coeffs(self):
+        """the six Fq2 coefficients in the reference's flat (ZT) order"""
+        return [self.c0.a0, self.c0.a1, self.c0.a2, self.c1.a0, self.c1.a1, self.c1.a2]
+
+    @staticmethod
+    def from_coeffs(c):
+        return F12(F6(c[0], c[1], c[2]), F6(c[3], c[4], c[5]))
+
+    def __add__(self, o):
+        return F12(self.c0 + o.c0, self.c1 + o.c1)
+
+    def __sub__(self, o):
+        return F12(self.c0 - o.c0, self.c1 - o.c1)
+
+    def __neg__(self):
+        return F12(-self.c0, -self.c1)
+
+    def __mul__(self, o):
+        t0 = self.c0 * o.c0
+        t1 = self.c1 * o.c1
+        c1 = (self.c0 + self.c1) * (o.c0 + o.c1) - t0 - t1
+        return F12(t0 + t1.mul_v(), c1)
+
+    def sqr(self):
+        a0, a1 = self.c0, self.c1
+        t = a0 * a1
+        c0 = (a0 + a1) * (a0 + a1.mul_v()) - t - t.mul_v()
+        return F12(c0, t.dbl())
+
+    def conj(self):
+        """x^(q^6)"""
+        return F12(self.c0, -self.c1)
+
+    def mul_by_014(self, l0, l1, l4):
+        """times the sparse line value (l0 + l1 v) + (l4 v) w"""
+        t0 = self.c0.mul_by_01(l0, l1)
+        t1 = self.c1.mul_by_1(l4)
+        c1 = (self.c0 + self.c1).mul_by_01(l0, l1 + l4) - t0 - t1
+        return F12(t0 + t1.mul_v(), c1)
+
+    def inv(self, fp_inv):
+        """(c0 - c1 w) / (c0^2 - v c1^2)  (bls_py/fields_t.py:328-337)"""
+        t = (self.c0.sqr() - self.c1.sqr().mul_v()).inv(fp_inv)
+        return F12(self.c0 * t, -(self.c1 * t))
+
+    def frob(self, prog, i):
+        """x^(q^i) for i in (1, 2, 3)  (bls_py/fields_t.py:355-364)"""
+        gam = frob_gamma(i)
+        c = self.coeffs()
+        w_of = [0, 2, 4, 1, 3, 5]           # flat coefficient p multiplies w^(w_of[p])
+        out = []
+        for p in range(6):
+            x = c[p].conj() if (i & 1) else c[p]
+            g = gam[w_of[p]]
+            if g == (1, 0):
+                out.append(x)
+            elif g[1] == 0:
+                out.append(x * prog.const1(g[0]))
+            else:
+                out.append(x * prog.const2(g))
+        return F12.from_coeffs(out)
+
+
+def f12_one(prog):
+    one = prog.const2((1, 0))
+    zero = prog.const2((0, 0))
+    return F12(F6(one, zero, zero), F6(zero, zero, zero))
+
+
+def fp_pow_chain(prog, a, e, window=4):
+    """a^e for a fixed exponent e > 0: left-to-right sliding window over Fq cells.
+    The odd-power table is packed two entries per Fq2 cell pair."""
+    if e == 1:
+        return a
+    nt = 1 << (window - 1)
+    bits = bin(e)[2:]
+    # which odd powers are actually needed
+    i, need, plan = 0, set(), []
+    while i < len(bits):
+        if bits[i] == "0":
+            plan.append(("s", 1))
+            i += 1
+            continue
+        j = min(i + window, len(bits))
+        while bits[j - 1] == "0":
+            j -= 1
+        val = int(bits[i:j], 2)
+        plan.append(("m", j - i, val))
+        need.add(val)
+        i = j
+    top = max(need)
+    table = {1: a}
+    if top > 1:
+        a2 = a.sqr()
+        prev = a
+        packs = []
+        pending = None
+        for k in range(3, top + 1, 2):
+            prev = prev * a2
+            if pending is None:
+                pending = (k, prev)
+            else:
+                pk = prog.pack(pending[1], prev)
+                table[pending[0]] = pk.c0
+                table[k] = pk.c1
+                pending = None
+        if pending is not None:
+            table[pending[0]] = pending[1]
+    acc = None
+    for step in plan:
+        if step[0] == "s":
+            if acc is not None:
+                acc = acc.sqr()
+        else:
+            _, n, val = step
+            if acc is None:
+                acc = table[val]
+            else:
+                for _ in range(n):
+                    acc = acc.sqr()
+                acc = acc * table[val]
+    return acc
+
+
+def fp_inv_fermat(prog):
+    """returns a function a -> a^(q-2) (0 -> 0, like bls_py/fields_t.py:47-55)"""
+    return lambda a: fp_pow_chain(prog, a, Q - 2)

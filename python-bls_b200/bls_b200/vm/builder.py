@@ -1,0 +1,557 @@
+"""Program builder for the b200-bls field VM.
+
+Formulas are written in ordinary Python on symbolic values (``V2`` = an Fq2 element,
+``V1`` = an Fq element, ``Flag`` = a per-thread predicate); every operator appends one
+virtual instruction to the program.  ``Program.assemble`` then assigns shared-memory
+cells with a Belady-style linear scan (values are single-assignment, the code is straight
+line), inserting SPILL2/FILL2 moves to the global-memory cold area when the per-thread
+workspace is exceeded, and emits the 8-byte instructions the CUDA kernel interprets.
+"""
+import numpy as np
+
+from . import isa
+
+Q = int("1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f624"
+        "1eabfffeb153ffffb9feffffffffaaab", 16)
+
+
+class Val:
+    __slots__ = ("prog", "id", "width")
+
+    def __init__(self, prog, width):
+        self.prog = prog
+        self.width = width
+        self.id = prog._new_id(self)
+
+
+class V1(Val):
+    """Fq value (one cell)."""
+    __slots__ = ()
+
+    def __init__(self, prog):
+        super().__init__(prog, 1)
+
+    def _bin(self, op, other):
+        r = V1(self.prog)
+        self.prog.emit(op, r, self, other)
+        return r
+
+    def __add__(self, o):
+        return self._bin("ADD1", o)
+
+    def __sub__(self, o):
+        return self._bin("SUB1", o)
+
+    def __mul__(self, o):
+        if isinstance(o, (V2,)):
+            return o * self
+        return self._bin("MUL1", o)
+
+    def __neg__(self):
+        r = V1(self.prog)
+        self.prog.emit("NEG1", r, self)
+        return r
+
+    def sqr(self):
+        r = V1(self.prog)
+        self.prog.emit("SQR1", r, self)
+        return r
+
+    def dbl(self):
+        r = V1(self.prog)
+        self.prog.emit("DBL1", r, self)
+        return r
+
+    def is_zero(self):
+        f = Flag(self.prog)
+        self.prog.emit("FZERO1", f, self)
+        return f
+
+    def gt_half(self):
+        f = Flag(self.prog)
+        self.prog.emit("FGTHALF", f, self)
+        return f
+
+    def eq(self, o):
+        f = Flag(self.prog)
+        self.prog.emit("FEQ1", f, self, o)
+        return f
+
+
+class Half:
+    """Read (or initialising write) view of one coefficient of a V2."""
+    __slots__ = ("parent", "half", "prog", "width")
+
+    def __init__(self, parent, half):
+        self.parent = parent
+        self.half = half
+        self.prog = parent.prog
+        self.width = 1
+
+    # a Half behaves like a V1 source
+    __add__ = V1.__add__
+    __sub__ = V1.__sub__
+    __mul__ = V1.__mul__
+    __neg__ = V1.__neg__
+    _bin = V1._bin
+    sqr = V1.sqr
+    dbl = V1.dbl
+    is_zero = V1.is_zero
+    gt_half = V1.gt_half
+    eq = V1.eq
+
+
+class V2(Val):
+    """Fq2 value (an even/odd cell pair)."""
+    __slots__ = ()
+
+    def __init__(self, prog):
+        super().__init__(prog, 2)
+
+    @property
+    def c0(self):
+        return Half(self, 0)
+
+    @property
+    def c1(self):
+        return Half(self, 1)
+
+    def _bin(self, op, other):
+        r = V2(self.prog)
+        self.prog.emit(op, r, self, other)
+        return r
+
+    def _un(self, op):
+        r = V2(self.prog)
+        self.prog.emit(op, r, self)
+        return r
+
+    def __add__(self, o):
+        return self._bin("ADD2", o)
+
+    def __sub__(self, o):
+        return self._bin("SUB2", o)
+
+    def __mul__(self, o):
+        if isinstance(o, (V1, Half)):
+            return self._bin("MULFP2", o)
+        return self._bin("MUL2", o)
+
+    def __neg__(self):
+        return self._un("NEG2")
+
+    def sqr(self):
+        return self._un("SQR2")
+
+    def dbl(self):
+        return self._un("DBL2")
+
+    def mul_xi(self):
+        return self._un("MULXI2")
+
+    def conj(self):
+        return self._un("CONJ2")
+
+    def is_zero(self):
+        f = Flag(self.prog)
+        self.prog.emit("FZERO2", f, self)
+        return f
+
+    def eq(self, o):
+        f = Flag(self.prog)
+        self.prog.emit("FEQ2", f, self, o)
+        return f
+
+
+class Flag(Val):
+    __slots__ = ()
+
+    def __init__(self, prog):
+        super().__init__(prog, 0)
+
+    def _bin(self, op, o):
+        f = Flag(self.prog)
+        self.prog.emit(op, f, self, o)
+        return f
+
+    def __and__(self, o):
+        return self._bin("FAND", o)
+
+    def __or__(self, o):
+        return self._bin("FOR", o)
+
+    def __xor__(self, o):
+        return self._bin("FXOR", o)
+
+    def __invert__(self):
+        f = Flag(self.prog)
+        self.prog.emit("FNOT", f, self)
+        return f
+
+
+class VOp:
+    __slots__ = ("name", "d", "a", "b", "aux")
+
+    def __init__(self, name, d, a, b, aux):
+        self.name, self.d, self.a, self.b, self.aux = name, d, a, b, aux
+
+
+def _is_val(x):
+    return isinstance(x, (Val, Half))
+
+
+class Program:
+    """A straight-line VM program in three sections (prologue / per-item body / epilogue)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.vals = []
+        self.ops = []                 # virtual ops
+        self.consts = []              # python ints (standard form)
+        self._const_idx = {}
+        self.section_marks = {"body": 0, "epilogue": None}
+        self.n_in = 0
+        self.n_out = 0
+        self.keep = []                # values that must survive to the end (epilogue use)
+        self.persistent = set()       # ids of multi-assignment variables
+
+    # ---- infrastructure -------------------------------------------------------------
+    def _new_id(self, v):
+        self.vals.append(v)
+        return len(self.vals) - 1
+
+    def emit(self, name, d=None, a=None, b=None, aux=None):
+        self.ops.append(VOp(name, d, a, b, aux))
+
+    def begin_body(self):
+        self.section_marks["body"] = len(self.ops)
+
+    def begin_epilogue(self):
+        self.section_marks["epilogue"] = len(self.ops)
+
+    # ---- constants --------------------------------------------------------------------
+    def _cidx(self, ints):
+        key = tuple(int(x) % Q for x in ints)
+        if key not in self._const_idx:
+            self._const_idx[key] = len(self.consts)
+            self.consts.extend(key)
+        return self._const_idx[key]
+
+    def const1(self, x):
+        r = V1(self)
+        self.emit("LDC1", r, self._cidx((x,)))
+        return r
+
+    def const2(self, x):
+        r = V2(self)
+        self.emit("LDC2", r, self._cidx(x))
+        return r
+
+    # ---- I/O ----------------------------------------------------------------------------
+    def load1_be48(self, buf, off_bytes):
+        assert off_bytes % 16 == 0
+        r = V1(self)
+        self.emit("LDBE48", r, buf, off_bytes // 16)
+        return r
+
+    def load2_be48(self, buf, off_bytes):
+        """two consecutive 48-byte big-endian coefficients -> Fq2"""
+        r = V2(self)
+        self.emit("LDBE48", Half(r, 0), buf, off_bytes // 16)
+        self.emit("LDBE48", Half(r, 1), buf, off_bytes // 16 + 3)
+        return r
+
+    def load1_be32(self, buf, off_bytes):
+        assert off_bytes % 16 == 0
+        r = V1(self)
+        self.emit("LDBE32", r, buf, off_bytes // 16)
+        return r
+
+    def store1_be48(self, buf, off_bytes, v):
+        self.emit("STBE48", buf, v, off_bytes // 16)
+
+    def store2_be48(self, buf, off_bytes, v):
+        self.emit("STBE48", buf, v.c0, off_bytes // 16)
+        self.emit("STBE48", buf, v.c1, off_bytes // 16 + 3)
+
+    def store_flag(self, buf, off_bytes, f):
+        self.emit("STFLAG", buf, f, off_bytes)
+
+    def load_raw2(self, buf, elem):
+        r = V2(self)
+        self.emit("LDRAW2", r, buf, elem)
+        return r
+
+    def store_raw2(self, buf, elem, v, block_only=False):
+        self.emit("STRAWB2" if block_only else "STRAW2", buf, v, elem)
+
+    # ---- misc -----------------------------------------------------------------------------
+    def pack(self, a, b):
+        r = V2(self)
+        self.emit("MOV1", Half(r, 0), a)
+        self.emit("MOV1", Half(r, 1), b)
+        return r
+
+    def mov1(self, a):
+        r = V1(self)
+        self.emit("MOV1", r, a)
+        return r
+
+    def sel2(self, f, a, b):
+        r = V2(self)
+        self.emit("CSEL2", r, a, b, aux=f)
+        return r
+
+    def sel1(self, f, a, b):
+        r = V1(self)
+        self.emit("CSEL1", r, a, b, aux=f)
+        return r
+
+    def flag_const(self, bit):
+        f = Flag(self)
+        self.emit("FSET", f, int(bit))
+        return f
+
+    def flag_bit(self, buf, bit):
+        f = Flag(self)
+        self.emit("FBIT", f, buf, bit)
+        return f
+
+    def flag_byte(self, buf, off):
+        f = Flag(self)
+        self.emit("FLDB", f, buf, off)
+        return f
+
+    def flag_active(self):
+        f = Flag(self)
+        self.emit("FACTIVE", f)
+        return f
+
+    def var2(self, init):
+        """persistent (multi-assignment) Fq2 variable: keeps one fixed cell pair for the whole
+        program, e.g. an accumulator carried across item-loop iterations"""
+        r = V2(self)
+        self.emit("MOV2", r, init)
+        self.persistent.add(r.id)
+        return r
+
+    def assign(self, var, value):
+        assert var.id in self.persistent
+        self.emit("MOV2", var, value)
+
+    def sync(self):
+        self.emit("SYNC")
+
+    def xmov2(self, v, lane_off):
+        r = V2(self)
+        self.emit("XMOV2", r, v, lane_off)
+        return r
+
+    # ---- assembly ---------------------------------------------------------------------------
+    def assemble(self, n_slots, n_cold=1024):
+        return _assemble(self, n_slots, n_cold)
+
+
+class Assembled:
+    """Concrete program: ``code`` is an (n, 4) uint16 array [op|aux<<8, d, a, b]."""
+
+    def __init__(self, name, code, consts, marks, n_slots, n_cold, stats):
+        self.name = name
+        self.code = code
+        self.consts = consts
+        self.body_start, self.epilogue_start = marks
+        self.n_slots = n_slots
+        self.n_cold = n_cold
+        self.stats = stats
+
+    def const_limbs(self):
+        """constant table as Montgomery-form little-endian u32 limbs, shape (n, 12)"""
+        out = np.zeros((max(1, len(self.consts)), 12), dtype=np.uint32)
+        for i, c in enumerate(self.consts):
+            m = (c << 384) % Q
+            for j in range(12):
+                out[i, j] = (m >> (32 * j)) & 0xffffffff
+        return out
+
+
+def _assemble(prog, n_slots, n_cold):
+    ops = prog.ops
+    n = len(ops)
+    INF = 1 << 60
+
+    def root(x):
+        return x.parent if isinstance(x, Half) else x
+
+    # use positions per value
+    uses = {}
+    for i, op in enumerate(ops):
+        for x in (op.d, op.a, op.b, op.aux):
+            if _is_val(x):
+                uses.setdefault(root(x).id, []).append(i)
+    for v in prog.keep:
+        uses.setdefault(v.id, []).append(n)
+    use_ptr = {k: 0 for k in uses}
+    # values that cross the prologue/body boundary (or are persistent variables) keep a fixed
+    # cell for the whole program: the body is executed many times with the same assignment
+    body0 = prog.section_marks["body"]
+    fixed = set(prog.persistent)
+    for vid, lst in uses.items():
+        if lst[0] < body0 <= lst[-1] and body0 > 0:
+            fixed.add(vid)
+
+    def next_use(vid, after):
+        lst = uses[vid]
+        p = use_ptr[vid]
+        while p < len(lst) and lst[p] <= after:
+            p += 1
+        use_ptr[vid] = p
+        return lst[p] if p < len(lst) else INF
+
+    free_slots = list(range(n_slots - 1, -1, -1))
+    slot_of = {}          # value id -> slot (resident)
+    cold_of = {}          # value id -> cold index (has a valid cold copy)
+    free_cold = list(range(n_cold - 1, -1, -1))
+    free_flags = list(range(isa.N_FLAGS - 1, -1, -1))
+    flag_of = {}
+    out = []
+    stats = {"spills": 0, "fills": 0, "max_slots": 0, "max_cold": 0}
+
+    def emit(name, d=0, a=0, b=0, aux=0):
+        out.append((isa.OPCODE[name] | (aux << 8), d, a, b))
+
+    def alloc_slot(i, pinned):
+        if free_slots:
+            s = free_slots.pop()
+            stats["max_slots"] = max(stats["max_slots"], n_slots - len(free_slots))
+            return s
+        # evict the resident value with the farthest next use
+        best, best_use = None, -1
+        for vid in slot_of:
+            if vid in pinned or vid in fixed:
+                continue
+            nu = next_use(vid, i - 1)
+            if nu > best_use:
+                best, best_use = vid, nu
+        if best is None:
+            raise RuntimeError("workspace too small: all %d slots pinned at op %d (%s)"
+                               % (n_slots, i, ops[i].name))
+        s = slot_of.pop(best)
+        if best_use < INF and best not in cold_of:
+            if not free_cold:
+                raise RuntimeError("cold area exhausted")
+            c = free_cold.pop()
+            cold_of[best] = c
+            stats["max_cold"] = max(stats["max_cold"], n_cold - len(free_cold))
+            emit("SPILL2", c, 2 * s)
+            stats["spills"] += 1
+        return s
+
+    def release(vid):
+        if vid in fixed:
+            return
+        if vid in slot_of:
+            free_slots.append(slot_of.pop(vid))
+        if vid in cold_of:
+            free_cold.append(cold_of.pop(vid))
+
+    marks = [None, None]
+    for i, op in enumerate(ops):
+        if i == prog.section_marks["body"]:
+            marks[0] = len(out)
+        if i == prog.section_marks["epilogue"]:
+            marks[1] = len(out)
+        sig = isa.OPSIG[op.name]
+        fields = [op.d, op.a, op.b]
+        srcs = [x for x in (op.a, op.b) if _is_val(x) and not isinstance(root(x), Flag)]
+        # STBE48/STRAW2/SPILL-like ops read their 'a'; dst-position value operands that are
+        # data sources do not exist in this ISA (buffer ids are ints)
+        pinned = set(root(x).id for x in srcs)
+        d_is_data = _is_val(op.d) and not isinstance(root(op.d), Flag)
+        partial_def = d_is_data and isinstance(op.d, Half)
+        if partial_def and root(op.d).id in slot_of:
+            pinned.add(root(op.d).id)
+        # make sources resident
+        for x in srcs:
+            vid = root(x).id
+            if vid not in slot_of:
+                if vid not in cold_of:
+                    raise RuntimeError("use of undefined value at op %d (%s)" % (i, op.name))
+                s = alloc_slot(i, pinned)
+                slot_of[vid] = s
+                emit("FILL2", 2 * s, cold_of[vid])
+                stats["fills"] += 1
+        # concrete source operands
+        conc = [0, 0, 0]
+        for k, x in enumerate(fields):
+            if k == 0:
+                continue
+            if _is_val(x):
+                r = root(x)
+                if isinstance(r, Flag):
+                    conc[k] = flag_of[r.id]
+                else:
+                    conc[k] = 2 * slot_of[r.id] + (x.half if isinstance(x, Half) else 0)
+            elif x is not None:
+                conc[k] = int(x)
+        aux = 0
+        if op.aux is not None:
+            aux = flag_of[op.aux.id] if _is_val(op.aux) else int(op.aux)
+        # free sources that die here (so the destination can reuse their cells), except for
+        # cross-thread reads where other threads still read the source after we write
+        dying = []
+        for x in list(srcs) + [y for y in (op.a, op.b, op.aux) if _is_val(y) and isinstance(root(y), Flag)]:
+            vid = root(x).id
+            if vid not in dying and vid not in fixed and next_use(vid, i) == INF:
+                dying.append(vid)
+        if op.name != "XMOV2":
+            for vid in dying:
+                if vid in flag_of:
+                    pass
+                else:
+                    release(vid)
+        # destination
+        if _is_val(op.d):
+            r = root(op.d)
+            if isinstance(r, Flag):
+                if r.id not in flag_of:
+                    if not free_flags:
+                        raise RuntimeError("out of flags")
+                    flag_of[r.id] = free_flags.pop()
+                conc[0] = flag_of[r.id]
+            else:
+                if r.id not in slot_of:
+                    if r.id in cold_of:          # partial def of a spilled value: bring it back
+                        s = alloc_slot(i, pinned)
+                        slot_of[r.id] = s
+                        emit("FILL2", 2 * s, cold_of[r.id])
+                        stats["fills"] += 1
+                    else:
+                        slot_of[r.id] = alloc_slot(i, pinned)
+                if r.id in cold_of:              # cold copy goes stale on a (partial) write
+                    free_cold.append(cold_of.pop(r.id))
+                conc[0] = 2 * slot_of[r.id] + (op.d.half if isinstance(op.d, Half) else 0)
+        elif op.d is not None:
+            conc[0] = int(op.d)
+        emit(op.name, conc[0], conc[1], conc[2], aux)
+        if op.name == "XMOV2":
+            for vid in dying:
+                release(vid)
+        for vid in dying:
+            if vid in flag_of:
+                free_flags.append(flag_of.pop(vid))
+        # a destination that is never used is dead immediately
+        if _is_val(op.d):
+            r = root(op.d)
+            if r.id not in fixed and next_use(r.id, i) == INF:
+                if isinstance(r, Flag):
+                    if r.id in flag_of:
+                        free_flags.append(flag_of.pop(r.id))
+                else:
+                    release(r.id)
+    if marks[0] is None:
+        marks[0] = 0
+    if marks[1] is None:
+        marks[1] = len(out)
+    code = np.array(out, dtype=np.uint16).reshape(-1, 4)
+    stats["n_ins"] = len(out)
+    return Assembled(prog.name, code, list(prog.consts), tuple(marks), n_slots, n_cold, stats)

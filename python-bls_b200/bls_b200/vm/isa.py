@@ -1,0 +1,75 @@
+"""Instruction set of the b200-bls field VM (mirrored by csrc/vm_isa.h -- generated).
+
+One instruction is 8 bytes: ``u16 op | aux << 8``, ``u16 d``, ``u16 a``, ``u16 b``.
+Operands are *fp cell* indices in the thread's shared-memory workspace (an Fp2 value
+occupies an even/odd cell pair), constant-table indices, flag numbers, input/output
+buffer numbers or small immediates, depending on the opcode.
+"""
+
+OPS = [
+    # name        operand kinds (d, a, b)   -- c2/c1 = Fp2/Fp cell, k = const idx,
+    #                                           f = flag, u = buffer, i = immediate
+    ("NOP", "", ""),
+    ("MUL2", "c2 c2 c2", "d = a * b in Fq2"),
+    ("SQR2", "c2 c2 -", "d = a^2"),
+    ("ADD2", "c2 c2 c2", ""),
+    ("SUB2", "c2 c2 c2", ""),
+    ("NEG2", "c2 c2 -", ""),
+    ("DBL2", "c2 c2 -", "d = 2a"),
+    ("MULXI2", "c2 c2 -", "d = a * (1 + u)"),
+    ("CONJ2", "c2 c2 -", "d = (a.c0, -a.c1)"),
+    ("MOV2", "c2 c2 -", ""),
+    ("MULFP2", "c2 c2 c1", "d = a * b, b in Fq"),
+    ("MUL1", "c1 c1 c1", ""),
+    ("SQR1", "c1 c1 -", ""),
+    ("ADD1", "c1 c1 c1", ""),
+    ("SUB1", "c1 c1 c1", ""),
+    ("NEG1", "c1 c1 -", ""),
+    ("DBL1", "c1 c1 -", ""),
+    ("MOV1", "c1 c1 -", ""),
+    ("LDC1", "c1 k -", "d = const[a]"),
+    ("LDC2", "c2 k -", "d = (const[a], const[a+1])"),
+    ("FZERO1", "f c1 -", "flag[d] = (a == 0)"),
+    ("FZERO2", "f c2 -", ""),
+    ("FGTHALF", "f c1 -", "flag[d] = standard-form(a) > (q-1)/2"),
+    ("FEQ1", "f c1 c1", ""),
+    ("FEQ2", "f c2 c2", ""),
+    ("FAND", "f f f", ""),
+    ("FOR", "f f f", ""),
+    ("FXOR", "f f f", ""),
+    ("FNOT", "f f -", ""),
+    ("FSET", "f i -", "flag[d] = a & 1"),
+    ("FBIT", "f u i", "flag[d] = bit b of the item's 32-byte big-endian scalar in buffer a"),
+    ("FACTIVE", "f - -", "flag[d] = item index < n_items"),
+    ("CSEL2", "c2 c2 c2", "d = flag[aux] ? a : b"),
+    ("CSEL1", "c1 c1 c1", ""),
+    ("LDBE48", "c1 u i", "d = to_mont(48 big-endian bytes at buffer a, byte offset 16*b)"),
+    ("LDBE32", "c1 u i", "d = to_mont(32 big-endian bytes ...)"),
+    ("STBE48", "u c1 i", "buffer d, byte offset 16*b <- 48 big-endian bytes of from_mont(a)"),
+    ("STFLAG", "u f i", "buffer d, byte offset b <- flag[a] as one byte"),
+    ("LDRAW2", "c2 u i", "d = Montgomery limbs from internal SoA buffer a, element b"),
+    ("STRAW2", "u c2 i", "internal SoA buffer d, element b <- a"),
+    ("STRAWB2", "u c2 i", "as STRAW2 but only thread 0 of the block, item = block index"),
+    ("SPILL2", "g c2 -", "cold[d] <- a   (global-memory spill area)"),
+    ("FILL2", "c2 g -", "d <- cold[a]"),
+    ("SYNC", "- - -", "block barrier"),
+    ("XMOV2", "c2 c2 i", "d = cell a of thread (tid + b) mod block size"),
+    ("SKIPZ", "f i -", "if no thread of the warp has flag[d]: skip the next a instructions"),
+    ("FLDB", "f u i", "flag[d] = (byte b of the item's record in buffer a) != 0"),
+]
+
+OPCODE = {name: i for i, (name, _, _) in enumerate(OPS)}
+OPNAME = {i: name for name, i in OPCODE.items()}
+OPSIG = {name: sig.split() for name, sig, _ in OPS}
+
+N_FLAGS = 32
+INS_BYTES = 8
+
+
+def c_header():
+    lines = ["// generated from bls_b200/vm/isa.py -- do not edit", "#pragma once", "enum VmOp : int {"]
+    for i, (name, sig, doc) in enumerate(OPS):
+        lines.append("  OP_%s = %d,%s" % (name, i, ("  // " + (sig + "  " + doc).strip()) if (sig or doc) else ""))
+    lines.append("  OP__COUNT = %d" % len(OPS))
+    lines.append("};")
+    return "\n".join(lines) + "\n"

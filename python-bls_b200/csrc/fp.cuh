@@ -1,0 +1,371 @@
+// fp.cuh -- BLS12-381 base field Fq on 12 x 32-bit limbs, Montgomery form (R = 2^384).
+//
+// Device code is hand-written PTX carry chains: every 32x32->64 limb product is a
+// mad.lo.cc / madc.hi.cc pair that ptxas fuses into one IMAD.WIDE.U32 with a
+// predicate carry, accumulated into two interleaved ("even" / "odd" aligned)
+// 64-bit column sets so that no carry ever has to be rippled by hand.
+//
+// Replaces (reference, /root/reference): the Python big-int arithmetic behind
+// bls_py/fields.py:35-243 (class Fq) and the `% Q` reductions all over
+// bls_py/fields_t.py.  Values are always fully reduced to [0, q) so that equality and
+// zero tests are limb comparisons.
+//
+// The same header compiles for the host (B200BLS_HOSTSIM) with the PTX instructions
+// emulated one by one, carry flag included.  That build exists ONLY so that tests can
+// exercise the exact instruction sequences on the CPU-only development box
+// (tests/hostsim); the product library never contains or calls it.
+#pragma once
+#include <stdint.h>
+
+#ifdef B200BLS_HOSTSIM
+#define FP_DEV inline
+#define FP_CONST static const
+#else
+#define FP_DEV __device__ __forceinline__
+#define FP_CONST __device__ __constant__ const
+#endif
+
+namespace b200bls {
+
+constexpr int NL = 12;  // limbs
+
+struct fp {
+  uint32_t v[NL];
+};
+struct fp2 {
+  fp c0, c1;
+};
+
+// q, little-endian limbs
+#define B200BLS_Q_LIMBS                                                                        \
+  {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, \
+   0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau}
+constexpr uint32_t Q_INV_NEG = 0xfffcfffdu;  // -q^-1 mod 2^32
+
+#ifdef B200BLS_HOSTSIM
+static const uint32_t kQ[NL] = B200BLS_Q_LIMBS;
+#define QL(i) kQ[i]
+#else
+// Compile-time immediates: the modulus limbs become instruction immediates / constant
+// bank operands instead of live registers.
+__device__ __forceinline__ constexpr uint32_t q_limb(int i) {
+  constexpr uint32_t t[NL] = B200BLS_Q_LIMBS;
+  return t[i];
+}
+#define QL(i) q_limb(i)
+#endif
+
+// ---------------------------------------------------------------------------------------
+// PTX primitives (and their host emulation)
+// ---------------------------------------------------------------------------------------
+#ifdef B200BLS_HOSTSIM
+static thread_local uint32_t g_cf = 0;  // emulated CC.CF
+inline uint32_t add_cc(uint32_t a, uint32_t b) {
+  uint64_t s = (uint64_t)a + b;
+  g_cf = (uint32_t)(s >> 32);
+  return (uint32_t)s;
+}
+inline uint32_t addc_cc(uint32_t a, uint32_t b) {
+  uint64_t s = (uint64_t)a + b + g_cf;
+  g_cf = (uint32_t)(s >> 32);
+  return (uint32_t)s;
+}
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + g_cf; }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) {
+  uint64_t s = (uint64_t)a - b;
+  g_cf = (uint32_t)(s >> 63);  // borrow
+  return (uint32_t)s;
+}
+inline uint32_t subc_cc(uint32_t a, uint32_t b) {
+  uint64_t s = (uint64_t)a - b - g_cf;
+  g_cf = (uint32_t)(s >> 63);
+  return (uint32_t)s;
+}
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - g_cf; }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(a * b, c); }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(a * b, c); }
+inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return mul_hi(a, b) + c + g_cf; }
+#else
+// NB: borrow semantics of sub.cc/subc on the GPU: CC.CF holds the borrow.
+__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t sub_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+__device__ __forceinline__ uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
+// add / sub / neg (fully reduced in, fully reduced out)
+// ---------------------------------------------------------------------------------------
+FP_DEV void fp_set_zero(fp& r) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.v[i] = 0;
+}
+
+FP_DEV bool fp_is_zero(const fp& a) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) t |= a.v[i];
+  return t == 0;
+}
+
+FP_DEV bool fp_eq(const fp& a, const fp& b) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) t |= a.v[i] ^ b.v[i];
+  return t == 0;
+}
+
+// r = x - q if x >= q else x, for x < 2q given as 12 limbs
+FP_DEV void fp_cond_sub_q(fp& r, const fp& x) {
+  fp t;
+  t.v[0] = sub_cc(x.v[0], QL(0));
+#pragma unroll
+  for (int i = 1; i < NL; i++) t.v[i] = subc_cc(x.v[i], QL(i));
+  uint32_t borrow = subc(0, 0);  // 0xffffffff when x < q
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.v[i] = borrow ? x.v[i] : t.v[i];
+}
+
+FP_DEV void fp_add(fp& r, const fp& a, const fp& b) {
+  fp s;
+  s.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) s.v[i] = addc_cc(a.v[i], b.v[i]);
+  s.v[NL - 1] = addc(a.v[NL - 1], b.v[NL - 1]);  // 2q < 2^384: no carry out
+  fp_cond_sub_q(r, s);
+}
+
+FP_DEV void fp_sub(fp& r, const fp& a, const fp& b) {
+  fp d;
+  d.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < NL; i++) d.v[i] = subc_cc(a.v[i], b.v[i]);
+  uint32_t mask = subc(0, 0);  // all ones when a < b
+  r.v[0] = add_cc(d.v[0], QL(0) & mask);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) r.v[i] = addc_cc(d.v[i], QL(i) & mask);
+  r.v[NL - 1] = addc(d.v[NL - 1], QL(NL - 1) & mask);
+}
+
+FP_DEV void fp_neg(fp& r, const fp& a) {
+  uint32_t nz = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) nz |= a.v[i];
+  uint32_t mask = nz ? 0xffffffffu : 0u;
+  fp d;
+  d.v[0] = sub_cc(QL(0), a.v[0]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) d.v[i] = subc_cc(QL(i), a.v[i]);
+  d.v[NL - 1] = subc(QL(NL - 1), a.v[NL - 1]);
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.v[i] = d.v[i] & mask;
+}
+
+FP_DEV void fp_dbl(fp& r, const fp& a) { fp_add(r, a, a); }
+
+// a > b as plain 384-bit integers (used on values taken out of Montgomery form)
+FP_DEV bool fp_raw_gt(const fp& a, const fp& b) {
+  sub_cc(b.v[0], a.v[0]);
+#pragma unroll
+  for (int i = 1; i < NL; i++) subc_cc(b.v[i], a.v[i]);
+  return subc(0, 0) != 0;  // borrow <=> b < a
+}
+
+// ---------------------------------------------------------------------------------------
+// Montgomery multiplication: r = a * b / R mod q
+//
+// State T = E + O * 2^32.  E = ev[0..11] holds 64-bit columns at even word positions,
+// O = od[0..11] the columns at odd positions (od[k] has weight 2^(32(k+1))).  One round
+// adds a * b_i and m * q to both sets with four carry chains of six lo/hi pairs each and
+// then divides by 2^32 by *renaming*: the odd set becomes the even set of the next round
+// and the even set, shifted down two words, becomes the odd one.  The word that falls
+// between the two (ev[1]) is folded in by the first add of the next round, whose carry is
+// consumed by the following chain -- the trick known from CGBN / sppark's mont_t.
+// ---------------------------------------------------------------------------------------
+// acc[0..11] (+)= x[j] * y for j = start, start+2, ..., 6 columns; continues an open carry
+template <bool CARRY_IN>
+FP_DEV void mad_row(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+  for (int j = 0; j < NL; j += 2) {
+    if (j == 0 && !CARRY_IN)
+      acc[j] = mad_lo_cc(x[j], y, acc[j]);
+    else
+      acc[j] = madc_lo_cc(x[j], y, acc[j]);
+    acc[j + 1] = madc_hi_cc(x[j], y, acc[j + 1]);
+  }
+}
+
+// same with the constant modulus as multiplicand; OFF selects even (0) / odd (1) limbs
+template <int OFF>
+FP_DEV void mad_row_q(uint32_t* acc, uint32_t y) {
+#pragma unroll
+  for (int j = 0; j < NL; j += 2) {
+    if (j == 0)
+      acc[j] = mad_lo_cc(QL(j + OFF), y, acc[j]);
+    else
+      acc[j] = madc_lo_cc(QL(j + OFF), y, acc[j]);
+    acc[j + 1] = madc_hi_cc(QL(j + OFF), y, acc[j + 1]);
+  }
+}
+
+// acc_new[k] = acc[k+2] + x[j]*y columns, i.e. accumulate while shifting down two words;
+// starts with an incoming carry (from the fold of the dropped word)
+FP_DEV void madc_row_rshift(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+  for (int j = 0; j < NL - 2; j += 2) {
+    acc[j] = madc_lo_cc(x[j], y, acc[j + 2]);
+    acc[j + 1] = madc_hi_cc(x[j], y, acc[j + 3]);
+  }
+  acc[NL - 2] = madc_lo_cc(x[NL - 2], y, 0);
+  acc[NL - 1] = madc_hi(x[NL - 2], y, 0);
+}
+
+FP_DEV void mont_round_first(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < NL; j += 2) {
+    ev[j] = mul_lo(a[j], bi);
+    ev[j + 1] = mul_hi(a[j], bi);
+    od[j] = mul_lo(a[j + 1], bi);
+    od[j + 1] = mul_hi(a[j + 1], bi);
+  }
+  uint32_t m = mul_lo(ev[0], Q_INV_NEG);
+  mad_row_q<1>(od, m);  // no carry out: T < 2^(32*13)
+  mad_row_q<0>(ev, m);
+  od[NL - 1] = addc(od[NL - 1], 0);
+}
+
+// ev: set that is even-aligned in THIS round; od: last round's even set (od[0] == 0,
+// od[1] is the word to fold, od[2..] become this round's odd columns)
+FP_DEV void mont_round(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi) {
+  ev[0] = add_cc(ev[0], od[1]);
+  madc_row_rshift(od, a + 1, bi);
+  mad_row<false>(ev, a, bi);
+  od[NL - 1] = addc(od[NL - 1], 0);
+  uint32_t m = mul_lo(ev[0], Q_INV_NEG);
+  mad_row_q<1>(od, m);
+  mad_row_q<0>(ev, m);
+  od[NL - 1] = addc(od[NL - 1], 0);
+}
+
+FP_DEV void fp_mul(fp& r, const fp& a, const fp& b) {
+  uint32_t ev[NL], od[NL];
+  mont_round_first(ev, od, a.v, b.v[0]);
+#pragma unroll
+  for (int i = 1; i < NL; i += 2) {
+    mont_round(od, ev, a.v, b.v[i]);
+    if (i + 1 < NL) mont_round(ev, od, a.v, b.v[i + 1]);
+  }
+  // 12 rounds: the last one ran with (od, ev) roles, so `od` was the even-aligned set
+  // (od[0] == 0 now) and `ev` holds the odd columns: T / 2^32 = ev + (od >> one word)
+  fp t;
+  t.v[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) t.v[i] = addc_cc(ev[i], od[i + 1]);
+  t.v[NL - 1] = addc(ev[NL - 1], 0);
+  fp_cond_sub_q(r, t);
+}
+
+FP_DEV void fp_sqr(fp& r, const fp& a) { fp_mul(r, a, a); }
+
+// ---------------------------------------------------------------------------------------
+// Fq2 = Fq[u]/(u^2+1)  (reference: bls_py/fields.py:321-482, fields_t.py:75-161)
+// ---------------------------------------------------------------------------------------
+FP_DEV void fp2_add(fp2& r, const fp2& a, const fp2& b) {
+  fp_add(r.c0, a.c0, b.c0);
+  fp_add(r.c1, a.c1, b.c1);
+}
+FP_DEV void fp2_sub(fp2& r, const fp2& a, const fp2& b) {
+  fp_sub(r.c0, a.c0, b.c0);
+  fp_sub(r.c1, a.c1, b.c1);
+}
+FP_DEV void fp2_neg(fp2& r, const fp2& a) {
+  fp_neg(r.c0, a.c0);
+  fp_neg(r.c1, a.c1);
+}
+// Karatsuba, 3 base multiplications (fields_t.py:157-161 uses 4)
+FP_DEV void fp2_mul(fp2& r, const fp2& a, const fp2& b) {
+  fp sa, sb, t0, t1, t2;
+  fp_add(sa, a.c0, a.c1);
+  fp_add(sb, b.c0, b.c1);
+  fp_mul(t0, a.c0, b.c0);
+  fp_mul(t1, a.c1, b.c1);
+  fp_mul(t2, sa, sb);
+  fp_sub(r.c0, t0, t1);
+  fp_sub(t2, t2, t0);
+  fp_sub(r.c1, t2, t1);
+}
+// (a0+a1)(a0-a1), 2 a0 a1
+FP_DEV void fp2_sqr(fp2& r, const fp2& a) {
+  fp s, d, p;
+  fp_add(s, a.c0, a.c1);
+  fp_sub(d, a.c0, a.c1);
+  fp_mul(p, a.c0, a.c1);
+  fp_mul(r.c0, s, d);
+  fp_add(r.c1, p, p);
+}
+// times xi = 1 + u  (fields_t.py:113-116)
+FP_DEV void fp2_mul_xi(fp2& r, const fp2& a) {
+  fp t;
+  fp_sub(t, a.c0, a.c1);
+  fp_add(r.c1, a.c0, a.c1);
+  r.c0 = t;
+}
+
+}  // namespace b200bls

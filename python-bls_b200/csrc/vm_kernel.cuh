@@ -1,0 +1,209 @@
+// vm_kernel.cuh -- the sm_100a kernel that interprets b200-bls field programs.
+//
+// Launch shape: one CTA of VM_NT threads per SM (persistent over the item loop), one batch
+// item (pairing, signature, point ...) per thread.  Each thread owns `n_slots` Fq2 slots
+// (2 fp cells each) of shared memory laid out [cell][16-byte chunk][thread], so a warp's
+// LDS.128/STS.128 touches 512 contiguous bytes: conflict free.  With 18 slots x 128 threads
+// the CTA uses 216 KB of the 227 KB carve-out; values that do not fit are spilled by the
+// program itself (SPILL2/FILL2) to a global-memory cold area laid out [slot][chunk][thread]
+// (fully coalesced, L2 resident).  The integer-multiply pipe is the roofline;
+// shared memory and L2 traffic are an order of magnitude below their limits.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "vm_exec.cuh"
+
+namespace b200bls {
+
+constexpr int VM_NT = 128;      // threads per CTA
+constexpr int VM_MAX_BUFS = 8;
+
+struct VmBuf {
+  unsigned char* ptr;
+  long long stride;  // bytes per item (byte buffers) or item capacity (raw SoA buffers)
+};
+
+struct VmParams {
+  const uint2* code;       // instructions, padded with one trailing NOP
+  int body_start, epi_start, n_ins;
+  const uint4* consts;     // Montgomery-form constants, 3 x uint4 each
+  uint4* cold;             // [n_cold * 6][total threads]
+  long long n_items;
+  long long iters;         // body repetitions = ceil(n_items / total threads)
+  VmBuf bufs[VM_MAX_BUFS];
+};
+
+struct DevEnv {
+  uint4* sm;               // shared workspace, already offset by threadIdx.x
+  const VmParams* p;
+  uint4* cold;             // cold area, already offset by the global thread id
+  long long total;
+  long long item_raw, item;
+  uint32_t flags;
+
+  __device__ __forceinline__ static void unpack(fp& x, int k, uint4 v) {
+    x.v[4 * k] = v.x;
+    x.v[4 * k + 1] = v.y;
+    x.v[4 * k + 2] = v.z;
+    x.v[4 * k + 3] = v.w;
+  }
+  __device__ __forceinline__ static uint4 pack(const fp& x, int k) {
+    return make_uint4(x.v[4 * k], x.v[4 * k + 1], x.v[4 * k + 2], x.v[4 * k + 3]);
+  }
+  __device__ __forceinline__ void ld1(int c, fp& x) {
+    const uint4* q = sm + c * (3 * VM_NT);
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x, k, q[k * VM_NT]);
+  }
+  __device__ __forceinline__ void st1(int c, const fp& x) {
+    uint4* q = sm + c * (3 * VM_NT);
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k * VM_NT] = pack(x, k);
+  }
+  __device__ __forceinline__ void ld2(int c, fp2& x) {
+    const uint4* q = sm + c * (3 * VM_NT);
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x.c0, k, q[k * VM_NT]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x.c1, k, q[(3 + k) * VM_NT]);
+  }
+  __device__ __forceinline__ void st2(int c, const fp2& x) {
+    uint4* q = sm + c * (3 * VM_NT);
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k * VM_NT] = pack(x.c0, k);
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[(3 + k) * VM_NT] = pack(x.c1, k);
+  }
+  __device__ __forceinline__ void ld2_lane(int c, int off, fp2& x) {
+    int t = (threadIdx.x + off) % VM_NT;
+    const uint4* q = sm - threadIdx.x + t + c * (3 * VM_NT);
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x.c0, k, q[k * VM_NT]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x.c1, k, q[(3 + k) * VM_NT]);
+  }
+  __device__ __forceinline__ void ldc(int idx, fp& x) {
+    const uint4* q = p->consts + idx * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x, k, __ldg(q + k));
+  }
+  __device__ __forceinline__ void set_flag(int f, bool v) {
+    flags = (flags & ~(1u << f)) | ((v ? 1u : 0u) << f);
+  }
+  __device__ __forceinline__ bool get_flag(int f) { return (flags >> f) & 1u; }
+  __device__ __forceinline__ bool any_flag(int f) { return __any_sync(0xffffffffu, (flags >> f) & 1u); }
+  __device__ __forceinline__ bool active() { return item_raw < p->n_items; }
+  __device__ __forceinline__ uint32_t ld_byte(int buf, int off) {
+    return p->bufs[buf].ptr[item * p->bufs[buf].stride + off];
+  }
+  __device__ __forceinline__ void st_byte(int buf, int off, unsigned char v) {
+    if (active()) p->bufs[buf].ptr[item * p->bufs[buf].stride + off] = v;
+  }
+  __device__ __forceinline__ void ld_be(int buf, int off, int nwords, fp& x) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p->bufs[buf].ptr + item * p->bufs[buf].stride + off);
+#pragma unroll
+    for (int i = 0; i < NL; i++) x.v[i] = 0;
+    if (nwords == 12) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) x.v[i] = __byte_perm(__ldg(w + 11 - i), 0, 0x0123);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) x.v[i] = __byte_perm(__ldg(w + 7 - i), 0, 0x0123);
+    }
+  }
+  __device__ __forceinline__ void st_be48(int buf, int off, const fp& x) {
+    if (!active()) return;
+    uint32_t* w = reinterpret_cast<uint32_t*>(p->bufs[buf].ptr + item * p->bufs[buf].stride + off);
+#pragma unroll
+    for (int i = 0; i < NL; i++) w[11 - i] = __byte_perm(x.v[i], 0, 0x0123);
+  }
+  __device__ __forceinline__ void ld_raw2(int buf, int elem, fp2& x) {
+    const uint4* q = reinterpret_cast<const uint4*>(p->bufs[buf].ptr) + (long long)elem * 6 * p->bufs[buf].stride + item;
+    long long s = p->bufs[buf].stride;
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x.c0, k, q[k * s]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x.c1, k, q[(3 + k) * s]);
+  }
+  __device__ __forceinline__ void st_raw2(int buf, int elem, const fp2& x, bool block_only) {
+    long long it;
+    if (block_only) {
+      if (threadIdx.x != 0) return;
+      it = blockIdx.x;
+    } else {
+      if (!active()) return;
+      it = item_raw;
+    }
+    long long s = p->bufs[buf].stride;
+    uint4* q = reinterpret_cast<uint4*>(p->bufs[buf].ptr) + (long long)elem * 6 * s + it;
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k * s] = pack(x.c0, k);
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[(3 + k) * s] = pack(x.c1, k);
+  }
+  __device__ __forceinline__ void st_cold(int g, const fp2& x) {
+    uint4* q = cold + (long long)g * 6 * total;
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k * total] = pack(x.c0, k);
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[(3 + k) * total] = pack(x.c1, k);
+  }
+  __device__ __forceinline__ void ld_cold(int g, fp2& x) {
+    const uint4* q = cold + (long long)g * 6 * total;
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x.c0, k, q[k * total]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) unpack(x.c1, k, q[(3 + k) * total]);
+  }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+__device__ __forceinline__ void vm_run_section(DevEnv& env, const uint2* code, int lo, int hi) {
+  int pc = lo;
+  if (pc >= hi) return;
+  uint2 ins = __ldg(code + pc);
+  while (pc < hi) {
+    uint2 nxt = __ldg(code + pc + 1);  // the program is padded: always readable
+    int skip = vm_exec(env, ins.x, ins.y);
+    if (skip) {
+      pc += 1 + skip;
+      if (pc < hi) nxt = __ldg(code + pc);
+    } else {
+      pc += 1;
+    }
+    ins = nxt;
+  }
+}
+
+__global__ void __launch_bounds__(VM_NT, 1) vm_kernel(const __grid_constant__ VmParams p) {
+  extern __shared__ uint4 vm_smem[];
+  DevEnv env;
+  env.sm = vm_smem + threadIdx.x;
+  env.p = &p;
+  env.total = (long long)gridDim.x * VM_NT;
+  const long long gtid = (long long)blockIdx.x * VM_NT + threadIdx.x;
+  env.cold = p.cold + gtid;
+  env.flags = 0;
+  const long long last = p.n_items > 0 ? p.n_items - 1 : 0;
+  env.item_raw = gtid;
+  env.item = gtid < last ? gtid : last;
+  // prologue once, body `iters` times, epilogue once -- one copy of the interpreter loop
+  for (long long rep = 0; rep < p.iters + 2; rep++) {
+    int lo, hi;
+    if (rep == 0) {
+      lo = 0;
+      hi = p.body_start;
+    } else if (rep <= p.iters) {
+      lo = p.body_start;
+      hi = p.epi_start;
+      env.item_raw = (rep - 1) * env.total + gtid;
+      env.item = env.item_raw < last ? env.item_raw : last;
+    } else {
+      lo = p.epi_start;
+      hi = p.n_ins;
+    }
+    vm_run_section(env, p.code, lo, hi);
+  }
+}
+
+}  // namespace b200bls

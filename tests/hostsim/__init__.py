@@ -1,0 +1,42 @@
+"""Builds and drives the host simulation of the VM (test infrastructure, see hostsim_vm.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(HERE, "_hostsim_vm.so")
+        srcs = [os.path.join(HERE, "hostsim_vm.cpp")]
+        deps = srcs + [os.path.join(HERE, "..", "..", "python-bls_b200", "csrc", f)
+                       for f in ("fp.cuh", "vm_exec.cuh", "gen/vm_isa.h", "gen/fp_consts.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so] + srcs)
+        _LIB = ctypes.CDLL(so)
+    return _LIB
+
+
+def run(asm, bufs, strides, n_items, n_blocks=1, nt=4):
+    """bufs: {id: np.uint8 array (modified in place)}; strides: {id: bytes per item, or item
+    capacity for raw SoA buffers}"""
+    code = np.ascontiguousarray(asm.code).view(np.uint32).reshape(-1)
+    consts = np.ascontiguousarray(asm.const_limbs())
+    ptrs = (ctypes.c_void_p * 8)()
+    st = (ctypes.c_long * 8)()
+    for i in range(8):
+        if i in bufs:
+            assert bufs[i].dtype == np.uint8 and bufs[i].flags["C_CONTIGUOUS"]
+            ptrs[i] = bufs[i].ctypes.data
+            st[i] = strides.get(i, 0)
+    rc = lib().hs_vm_run(code.ctypes.data_as(ctypes.c_void_p), len(asm.code), asm.body_start,
+                         asm.epilogue_start, consts.ctypes.data_as(ctypes.c_void_p),
+                         asm.n_slots, max(asm.stats["max_cold"], 1), ptrs, st,
+                         ctypes.c_long(n_items), n_blocks, nt)
+    assert rc == 0
+    return bufs

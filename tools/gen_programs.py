@@ -1,0 +1,64 @@
+#!/usr/bin/env python3
+"""Assemble every VM program and write csrc/gen/programs.bin (embedded into libb200bls.so).
+
+Blob layout (little endian):
+  char magic[8] = "B2BLSPRG"; u32 version; u32 n_programs;
+  n_programs x { char name[32]; u32 n_ins, body_start, epi_start, n_consts, n_slots, n_cold;
+                 u64 code_off, consts_off; }
+  code:   (n_ins + 1) x 8 bytes (one trailing NOP of padding)
+  consts: n_consts x 12 x u32 Montgomery-form limbs
+"""
+import os
+import struct
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "python-bls_b200"))
+from bls_b200.programs import registry                        # noqa: E402
+
+
+def main(out_path=None):
+    out_path = out_path or os.path.join(ROOT, "python-bls_b200", "csrc", "gen", "programs.bin")
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    progs = []
+    for name, builder in registry.PROGRAMS.items():
+        t = time.time()
+        asm = builder().assemble(registry.N_SLOTS)
+        print("%-22s %6d ins  spills %4d fills %4d cold %3d  (%.1fs)" % (
+            name, asm.stats["n_ins"], asm.stats["spills"], asm.stats["fills"],
+            asm.stats["max_cold"], time.time() - t))
+        progs.append((name, asm))
+    head = 16 + len(progs) * (32 + 6 * 4 + 2 * 8)
+    blobs = []
+    off = head
+    table = b""
+    for name, asm in progs:
+        code = np.concatenate([asm.code, np.zeros((1, 4), dtype=np.uint16)]).astype("<u2").tobytes()
+        consts = asm.const_limbs().astype("<u4").tobytes()
+        n_consts = max(1, len(asm.consts))
+        off = (off + 15) & ~15
+        code_off = off
+        off += len(code)
+        off = (off + 15) & ~15
+        consts_off = off
+        off += len(consts)
+        table += struct.pack("<32s6I2Q", name.encode(), len(asm.code), asm.body_start,
+                             asm.epilogue_start, n_consts, asm.n_slots,
+                             max(1, asm.stats["max_cold"]), code_off, consts_off)
+        blobs.append((code_off, code, consts_off, consts))
+    data = bytearray(off)
+    data[0:16] = struct.pack("<8sII", b"B2BLSPRG", 1, len(progs))
+    data[16:16 + len(table)] = table
+    for code_off, code, consts_off, consts in blobs:
+        data[code_off:code_off + len(code)] = code
+        data[consts_off:consts_off + len(consts)] = consts
+    with open(out_path, "wb") as fh:
+        fh.write(data)
+    print("wrote", out_path, len(data), "bytes")
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:])
