@@ -49,6 +49,11 @@ void b200bls_shutdown(void);
 const char* b200bls_last_error(void);
 int b200bls_sm_count(void);              /* SMs of the initialised device, 0 if none */
 int b200bls_sync(void);                  /* wait for the library stream */
+/* Launch shape: 1 = one 128-thread CTA per SM with 18 Fq2 workspace slots per thread,
+ * 2 = two co-resident CTAs per SM with 9 slots each (more latency hiding, more spills to
+ * the global cold area).  Default 1, or the environment variable B200BLS_CTAS_PER_SM. */
+int b200bls_set_ctas_per_sm(int n);
+int b200bls_get_ctas_per_sm(void);
 
 /* ---- device / pinned memory for resident-data pipelines and benchmarks ----------------- */
 void* b200bls_malloc(size_t bytes);

@@ -103,13 +103,14 @@ def _pow_bits(f, e, sqr):
     return acc
 
 
-def final_exponentiation(prog, f, cyclotomic_sqr=None):
+def final_exponentiation(prog, f, cyclotomic=True):
     """f^((q^12-1)/n) with the exact exponent (reference: fields_t.py:1124-1128)."""
     fp_inv = fp_inv_fermat(prog)
     # easy part: f^((q^6 - 1)(q^2 + 1))
     t = f.conj() * f.inv(fp_inv)
     m = t.frob(prog, 2) * t
-    sqr = cyclotomic_sqr or (lambda x: x.sqr())
+    # after the easy part m lies in the cyclotomic subgroup: cheap squarings, inverse = conj
+    sqr = (lambda x: x.cyclotomic_sqr()) if cyclotomic else (lambda x: x.sqr())
     # hard part: m^(y (a+1) (q-a) (a^2+q^2-1)) * m
     t1 = _pow_bits(m, Y_EXP, sqr)
     t2 = _pow_bits(t1, X_ABS, sqr) * t1                    # ^(a+1)

@@ -1,7 +1,11 @@
 """Name -> builder table of every VM program embedded into libb200bls.so."""
 from . import fieldops, pairing
 
-N_SLOTS = 18        # Fq2 slots per thread: 18 * 96 B * 128 threads = 216 KB of shared memory
+# Fq2 slots per thread.  One CTA of 128 threads per SM gets 18 slots (216 KB of shared memory);
+# two co-resident CTAs per SM get 9 slots each and hide each other's latencies.  Every program
+# is assembled for both shapes; the variant for n != 18 is named "<name>#<n>".
+N_SLOTS = 18
+SLOT_VARIANTS = (18, 9)
 
 PROGRAMS = {}
 for _level in (1, 2, 6, 12):

@@ -147,6 +147,28 @@ class F12:
         """x^(q^6)"""
         return F12(self.c0, -self.c1)
 
+    def cyclotomic_sqr(self):
+        """x^2 for x in the cyclotomic subgroup (x^(q^6+1) = 1, true after the easy part of
+        the final exponentiation): Granger-Scott squaring, 9 Fq2 squarings instead of 12
+        Fq2 products.  Fq12 is seen as three Fq4 = Fq2[s]/(s^2 - xi) components."""
+        def fp4_sqr(a, b):
+            t0, t1 = a.sqr(), b.sqr()
+            return t1.mul_xi() + t0, (a + b).sqr() - t0 - t1
+
+        z0, z4, z3 = self.c0.a0, self.c0.a1, self.c0.a2
+        z2, z1, z5 = self.c1.a0, self.c1.a1, self.c1.a2
+        t0, t1 = fp4_sqr(z0, z1)
+        r0 = (t0 - z0).dbl() + t0
+        r1 = (t1 + z1).dbl() + t1
+        t0, t1 = fp4_sqr(z2, z3)
+        t2, t3 = fp4_sqr(z4, z5)
+        r4 = (t0 - z4).dbl() + t0
+        r5 = (t1 + z5).dbl() + t1
+        t0 = t3.mul_xi()
+        r2 = (t0 + z2).dbl() + t0
+        r3 = (t2 - z3).dbl() + t2
+        return F12(F6(r0, r4, r3), F6(r2, r1, r5))
+
     def mul_by_014(self, l0, l1, l4):
         """times the sparse line value (l0 + l1 v) + (l4 v) w"""
         t0 = self.c0.mul_by_01(l0, l1)

@@ -339,6 +339,26 @@ class Program:
         assert var.id in self.persistent
         self.emit("MOV2", var, value)
 
+    def update_sel(self, var, f, a):
+        """var = f ? a : var, in place (var keeps its cells)"""
+        self.emit("CSEL2" if var.width == 2 else "CSEL1", var, a, var, aux=f)
+
+    def skip_unless(self, f):
+        """``with prog.skip_unless(f):`` -- the enclosed instructions are skipped by a warp in
+        which no thread has flag f.  Purely an optimisation: the region must only change
+        state through ``update_sel(..., f, ...)`` so that executing it with f clear is a
+        no-op for that thread.  The allocator refuses spills inside a region."""
+        prog = self
+
+        class _Region:
+            def __enter__(self_inner):
+                prog.emit("SKIPZ", f, None)
+
+            def __exit__(self_inner, *exc):
+                prog.emit("SKIP_END")
+                return False
+        return _Region()
+
     def sync(self):
         self.emit("SYNC")
 
@@ -420,6 +440,8 @@ def _assemble(prog, n_slots, n_cold):
         out.append((isa.OPCODE[name] | (aux << 8), d, a, b))
 
     def alloc_slot(i, pinned):
+        if not free_slots and skip_stack:
+            raise RuntimeError("spill needed inside a skip region (op %d)" % i)
         if free_slots:
             s = free_slots.pop()
             stats["max_slots"] = max(stats["max_slots"], n_slots - len(free_slots))
@@ -455,12 +477,17 @@ def _assemble(prog, n_slots, n_cold):
             free_cold.append(cold_of.pop(vid))
 
     marks = [None, None]
+    skip_stack = []
     for i, op in enumerate(ops):
         if i == prog.section_marks["body"]:
             marks[0] = len(out)
         if i == prog.section_marks["epilogue"]:
             marks[1] = len(out)
-        sig = isa.OPSIG[op.name]
+        if op.name == "SKIP_END":
+            at = skip_stack.pop()
+            w0, d, _, b = out[at]
+            out[at] = (w0, d, len(out) - at - 1, b)
+            continue
         fields = [op.d, op.a, op.b]
         srcs = [x for x in (op.a, op.b) if _is_val(x) and not isinstance(root(x), Flag)]
         # STBE48/STRAW2/SPILL-like ops read their 'a'; dst-position value operands that are
@@ -476,6 +503,8 @@ def _assemble(prog, n_slots, n_cold):
             if vid not in slot_of:
                 if vid not in cold_of:
                     raise RuntimeError("use of undefined value at op %d (%s)" % (i, op.name))
+                if skip_stack:
+                    raise RuntimeError("fill needed inside a skip region (op %d)" % i)
                 s = alloc_slot(i, pinned)
                 slot_of[vid] = s
                 emit("FILL2", 2 * s, cold_of[vid])
@@ -532,6 +561,8 @@ def _assemble(prog, n_slots, n_cold):
                 conc[0] = 2 * slot_of[r.id] + (op.d.half if isinstance(op.d, Half) else 0)
         elif op.d is not None:
             conc[0] = int(op.d)
+        if op.name == "SKIPZ":
+            skip_stack.append(len(out))
         emit(op.name, conc[0], conc[1], conc[2], aux)
         if op.name == "XMOV2":
             for vid in dying:

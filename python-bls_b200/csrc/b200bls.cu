@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -73,6 +74,7 @@ struct Context {
   size_t cold_bytes = 0;
   Staging staging[VM_MAX_BUFS];
   uint64_t launches = 0;
+  int ctas_per_sm = 1;   // 1: 18-slot programs, 2: the "#9" variants, two CTAs per SM
 };
 
 Context g_ctx;
@@ -91,11 +93,12 @@ int ensure_staging(int i, size_t bytes) {
   return 0;
 }
 
-// grid: one CTA per SM at most; fewer when the batch is small
+// grid: ctas_per_sm CTAs per SM at most; fewer when the batch is small
 int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int n_bufs, int grid_override = 0) {
   Context& c = g_ctx;
   long long blocks_needed = (long long)((n_items + VM_NT - 1) / VM_NT);
-  int grid = (int)(blocks_needed < c.sm_count ? blocks_needed : c.sm_count);
+  long long max_grid = (long long)c.sm_count * (pr.n_slots <= 9 ? 2 : 1);
+  int grid = (int)(blocks_needed < max_grid ? blocks_needed : max_grid);
   if (grid < 1) grid = 1;
   if (grid_override > 0) grid = grid_override;
   long long total = (long long)grid * VM_NT;
@@ -104,7 +107,7 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
     if (c.cold) cudaFree(c.cold);
     c.cold = nullptr;
     c.cold_bytes = 0;
-    size_t want = (size_t)pr.n_cold * 6 * sizeof(uint4) * (size_t)c.sm_count * VM_NT;
+    size_t want = (size_t)pr.n_cold * 6 * sizeof(uint4) * (size_t)max_grid * VM_NT;
     if (want < cold_need) want = cold_need;
     cudaError_t e = cudaMalloc(&c.cold, want);
     if (e != cudaSuccess) return fail(B200BLS_E_NOMEM, "cold area cudaMalloc(%zu) failed", want);
@@ -128,10 +131,12 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   return 0;
 }
 
-const DevProgram* find_program(const char* name) {
+const DevProgram* find_program(const char* base) {
+  std::string name(base);
+  if (g_ctx.ctas_per_sm == 2 && name.find('#') == std::string::npos) name += "#9";
   auto it = g_ctx.programs.find(name);
   if (it == g_ctx.programs.end()) {
-    fail(B200BLS_E_PROGRAM, "unknown program '%s'", name);
+    fail(B200BLS_E_PROGRAM, "unknown program '%s'", name.c_str());
     return nullptr;
   }
   return &it->second;
@@ -247,6 +252,8 @@ int b200bls_init(int device) {
     nm[32] = 0;
     c.programs[nm] = dp;
   }
+  const char* env = getenv("B200BLS_CTAS_PER_SM");
+  if (env && (env[0] == '1' || env[0] == '2')) c.ctas_per_sm = env[0] - '0';
   c.device = device;
   c.ready = true;
   return 0;
@@ -278,6 +285,15 @@ void b200bls_shutdown(void) {
 }
 
 int b200bls_sm_count(void) { return g_ctx.ready ? g_ctx.sm_count : 0; }
+
+int b200bls_set_ctas_per_sm(int n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (n != 1 && n != 2) return fail(B200BLS_E_ARG, "ctas_per_sm must be 1 or 2");
+  g_ctx.ctas_per_sm = n;
+  return 0;
+}
+
+int b200bls_get_ctas_per_sm(void) { return g_ctx.ctas_per_sm; }
 
 int b200bls_sync(void) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");

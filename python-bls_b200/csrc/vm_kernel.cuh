@@ -175,7 +175,7 @@ __device__ __forceinline__ void vm_run_section(DevEnv& env, const uint2* code, i
   }
 }
 
-__global__ void __launch_bounds__(VM_NT, 1) vm_kernel(const __grid_constant__ VmParams p) {
+__global__ void __launch_bounds__(VM_NT, 2) vm_kernel(const __grid_constant__ VmParams p) {
   extern __shared__ uint4 vm_smem[];
   DevEnv env;
   env.sm = vm_smem + threadIdx.x;

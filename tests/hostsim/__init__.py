@@ -22,7 +22,7 @@ def lib():
     return _LIB
 
 
-def run(asm, bufs, strides, n_items, n_blocks=1, nt=4):
+def run(asm, bufs, strides, n_items, n_blocks=1, nt=4, honor_skips=True):
     """bufs: {id: np.uint8 array (modified in place)}; strides: {id: bytes per item, or item
     capacity for raw SoA buffers}"""
     code = np.ascontiguousarray(asm.code).view(np.uint32).reshape(-1)
@@ -37,6 +37,6 @@ def run(asm, bufs, strides, n_items, n_blocks=1, nt=4):
     rc = lib().hs_vm_run(code.ctypes.data_as(ctypes.c_void_p), len(asm.code), asm.body_start,
                          asm.epilogue_start, consts.ctypes.data_as(ctypes.c_void_p),
                          asm.n_slots, max(asm.stats["max_cold"], 1), ptrs, st,
-                         ctypes.c_long(n_items), n_blocks, nt)
+                         ctypes.c_long(n_items), n_blocks, nt, int(honor_skips))
     assert rc == 0
     return bufs

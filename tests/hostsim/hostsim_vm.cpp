@@ -115,7 +115,8 @@ struct HostEnv {
 
 extern "C" int hs_vm_run(const uint32_t* code, int n_ins, int body_start, int epi_start,
                          const uint32_t* consts, int n_slots, int n_cold, uint8_t** bufs,
-                         const long* strides, long n_items, int n_blocks, int nt) {
+                         const long* strides, long n_items, int n_blocks, int nt,
+                         int honor_skips) {
   Shared sh;
   sh.consts = consts;
   for (int i = 0; i < 8; i++) { sh.bufs[i] = bufs[i]; sh.strides[i] = strides[i]; }
@@ -143,9 +144,19 @@ extern "C" int hs_vm_run(const uint32_t* code, int n_ins, int body_start, int ep
       long last = n_items > 0 ? n_items - 1 : 0;
       env[g].item = env[g].item_raw < last ? env[g].item_raw : last;
     }
-    for (int pc = lo; pc < hi; pc++) {
-      uint32_t w0 = code[2 * pc], w1 = code[2 * pc + 1];
-      for (int g = 0; g < sh.total; g++) vm_exec(env[g], w0, w1);
+    // blocks are independent; inside a block all threads step together and SKIPZ is decided
+    // block-wide (the block plays the role of the warp)
+    for (int blk = 0; blk < n_blocks; blk++) {
+      for (int pc = lo; pc < hi; pc++) {
+        uint32_t w0 = code[2 * pc], w1 = code[2 * pc + 1];
+        if ((w0 & 0xff) == OP_SKIPZ) {
+          bool any = false;
+          for (int t = 0; t < nt; t++) any = any || env[blk * nt + t].get_flag(w0 >> 16);
+          if (!any && honor_skips) pc += (int)(w1 & 0xffff);
+          continue;
+        }
+        for (int t = 0; t < nt; t++) vm_exec(env[blk * nt + t], w0, w1);
+      }
     }
   };
   run(0, body_start, 0);

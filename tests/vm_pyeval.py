@@ -39,7 +39,7 @@ def run(prog, bufs, n_items, n_threads=1, strides=None, out_bufs=None):
         for k in range(lo, hi):
             op = prog.ops[k]
             nm = op.name
-            if nm == "SYNC":
+            if nm in ("SYNC", "SKIPZ", "SKIP_END"):
                 continue
             if nm == "XMOV2":
                 vals = [list(get(state[(t + op.b) % n_threads], op.a)) for t in range(n_threads)]

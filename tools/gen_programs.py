@@ -24,13 +24,15 @@ def main(out_path=None):
     out_path = out_path or os.path.join(ROOT, "python-bls_b200", "csrc", "gen", "programs.bin")
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     progs = []
-    for name, builder in registry.PROGRAMS.items():
-        t = time.time()
-        asm = builder().assemble(registry.N_SLOTS)
-        print("%-22s %6d ins  spills %4d fills %4d cold %3d  (%.1fs)" % (
-            name, asm.stats["n_ins"], asm.stats["spills"], asm.stats["fills"],
-            asm.stats["max_cold"], time.time() - t))
-        progs.append((name, asm))
+    for base, builder in registry.PROGRAMS.items():
+        for n_slots in registry.SLOT_VARIANTS:
+            name = base if n_slots == registry.N_SLOTS else "%s#%d" % (base, n_slots)
+            t = time.time()
+            asm = builder().assemble(n_slots, n_cold=4096)
+            print("%-24s %6d ins  spills %5d fills %5d cold %3d  (%.1fs)" % (
+                name, asm.stats["n_ins"], asm.stats["spills"], asm.stats["fills"],
+                asm.stats["max_cold"], time.time() - t))
+            progs.append((name, asm))
     head = 16 + len(progs) * (32 + 6 * 4 + 2 * 8)
     blobs = []
     off = head
