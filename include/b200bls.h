@@ -51,7 +51,7 @@ int b200bls_sm_count(void);              /* SMs of the initialised device, 0 if 
 int b200bls_sync(void);                  /* wait for the library stream */
 /* Launch shape: 1 = one 128-thread CTA per SM with 18 Fq2 workspace slots per thread,
  * 2 = two co-resident CTAs per SM with 9 slots each (more latency hiding, more spills to
- * the global cold area).  Default 1, or the environment variable B200BLS_CTAS_PER_SM. */
+ * the global cold area).  Default 2 (measured faster, profiles/r1_call2_probe.log), or the environment variable B200BLS_CTAS_PER_SM. */
 int b200bls_set_ctas_per_sm(int n);
 int b200bls_get_ctas_per_sm(void);
 
@@ -107,6 +107,63 @@ int b200bls_final_exp_batch_dev(const void* in, void* out, size_t n);
  * (projective, denominator-free lines).  final_exp(out) is canonical. out: n x 576. */
 int b200bls_miller_loop_batch(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n);
 int b200bls_miller_loop_batch_dev(const void* P, const void* Q, void* out, size_t n);
+
+/* Product of Miller loops without the final exponentiation: stage one of
+ * fq_ate_pairing_multi (fields_t.py:1114-1121).  out: 576 bytes.  This (non-canonical)
+ * value is what ranks exchange in a multi-GPU ate_pairing_multi / aggregate verification:
+ * multiply the per-rank values (b200bls_field_op_batch level 12, mul), then
+ * b200bls_final_exp_batch once. */
+int b200bls_miller_product(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n);
+int b200bls_miller_product_dev(const void* P, const void* Q, void* out, size_t n);
+/* fq_ate_pairing_multi (fields_t.py:1114-1121; pairing.py:84-92 ate_pairing_multi):
+ * prod_i miller(P_i, Q_i), one final exponentiation.  out: 576 bytes. */
+int b200bls_pairing_multi(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n);
+int b200bls_pairing_multi_dev(const void* P, const void* Q, void* out, size_t n);
+
+/* ---- curve arithmetic (affine in, affine out; infinity = zero bytes) --------------------------
+ * G1 points 96 bytes, G2 points 192 bytes, scalars 32 bytes big-endian (any value < 2^256;
+ * the reference's `c % Q == 0 -> infinity` early-out, fields_t.py:710/729, only triggers for
+ * c = 0 in that range and 0 * P is infinity anyway). */
+/* fq_scalar_mult_jacobian / fq2_scalar_mult_jacobian + to_affine (fields_t.py:705-740,
+ * 609-632; ec.py:365-391 scalar_mult_jacobian; keys.py:119-132 get_public_key / sign). */
+int b200bls_g1_scalar_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint8_t* out, size_t n);
+int b200bls_g1_scalar_mul_batch_dev(const void* pts, const void* scalars, void* out, size_t n);
+int b200bls_g2_scalar_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint8_t* out, size_t n);
+int b200bls_g2_scalar_mul_batch_dev(const void* pts, const void* scalars, void* out, size_t n);
+/* fq_add_points_jacobian / fq2_add_points_jacobian + to_affine (fields_t.py:762-819;
+ * ec.py:315-342).  P + P doubles for G1 too (the reference's TypeError at fields_t.py:781 is
+ * a defect, not behaviour). */
+int b200bls_g1_add_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+int b200bls_g2_add_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+/* Sum of n points -> one point: the folds of BLS.aggregate_pub_keys(secure=False)
+ * (bls.py:204-223) and BLS.aggregate_sigs_simple (bls.py:13-26) as a strided per-thread
+ * fold + CTA tree + one final CTA.  n = 0 gives infinity. */
+int b200bls_g1_sum(const uint8_t* pts, uint8_t* out, size_t n);
+int b200bls_g1_sum_dev(const void* pts, void* out, size_t n);
+int b200bls_g2_sum(const uint8_t* pts, uint8_t* out, size_t n);
+int b200bls_g2_sum_dev(const void* pts, void* out, size_t n);
+/* PublicKey.from_bytes (keys.py:29-40) / Signature.from_bytes (signature.py:22-38):
+ * compressed 48 / 96 bytes -> affine 96 / 192 bytes.  ok[i] = 0 (and a zero point) where the
+ * reference raises ValueError('No sqrt exists' / 'No y for point x'). */
+int b200bls_g1_decompress_batch(const uint8_t* in, uint8_t* out, uint8_t* ok, size_t n);
+int b200bls_g2_decompress_batch(const uint8_t* in, uint8_t* out, uint8_t* ok, size_t n);
+/* AffinePoint.serialize (ec.py:94-111): affine -> compressed (x, top bit = lex_gt_neg). */
+int b200bls_g1_compress_batch(const uint8_t* in, uint8_t* out, size_t n);
+int b200bls_g2_compress_batch(const uint8_t* in, uint8_t* out, size_t n);
+
+/* ---- hashing and verification ------------------------------------------------------------------ */
+/* hash_to_point_prehashed_Fq2 (ec.py:528-550): n x 32-byte message hashes -> n x 192 bytes. */
+int b200bls_hash_to_g2_batch(const uint8_t* hashes, uint8_t* out, size_t n);
+int b200bls_hash_to_g2_batch_dev(const void* hashes, void* out, size_t n);
+/* n independent single-message verifications, the data-parallel core of BLS.verify
+ * (bls.py:154-201): ok[i] = (e(-G1, sig_i) * e(pk_i, H(mh_i)) == 1).
+ * pk: n x 96, mh: n x 32, sig: n x 192 (affine), ok: n bytes. */
+int b200bls_verify_batch(const uint8_t* pk, const uint8_t* mh, const uint8_t* sig, uint8_t* ok, size_t n);
+int b200bls_verify_batch_dev(const void* pk, const void* mh, const void* sig, void* ok, size_t n);
+/* One aggregate signature over n distinct message hashes (bls.py:194-201):
+ * *ok = (e(-G1, sig) * prod_i e(pk_i, H(mh_i)) == 1).  n + 1 Miller loops, one final
+ * exponentiation.  pks are the per-message public-key sums the host-side grouping produced. */
+int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok);
 
 #ifdef __cplusplus
 }

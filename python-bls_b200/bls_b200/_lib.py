@@ -49,6 +49,29 @@ def _load():
         "b200bls_final_exp_batch_dev": (i32, [vp, vp, sz]),
         "b200bls_miller_loop_batch": (i32, [vp, vp, vp, sz]),
         "b200bls_miller_loop_batch_dev": (i32, [vp, vp, vp, sz]),
+        "b200bls_miller_product": (i32, [vp, vp, vp, sz]),
+        "b200bls_miller_product_dev": (i32, [vp, vp, vp, sz]),
+        "b200bls_pairing_multi": (i32, [vp, vp, vp, sz]),
+        "b200bls_pairing_multi_dev": (i32, [vp, vp, vp, sz]),
+        "b200bls_g1_scalar_mul_batch": (i32, [vp, vp, vp, sz]),
+        "b200bls_g1_scalar_mul_batch_dev": (i32, [vp, vp, vp, sz]),
+        "b200bls_g2_scalar_mul_batch": (i32, [vp, vp, vp, sz]),
+        "b200bls_g2_scalar_mul_batch_dev": (i32, [vp, vp, vp, sz]),
+        "b200bls_g1_add_batch": (i32, [vp, vp, vp, sz]),
+        "b200bls_g2_add_batch": (i32, [vp, vp, vp, sz]),
+        "b200bls_g1_sum": (i32, [vp, vp, sz]),
+        "b200bls_g1_sum_dev": (i32, [vp, vp, sz]),
+        "b200bls_g2_sum": (i32, [vp, vp, sz]),
+        "b200bls_g2_sum_dev": (i32, [vp, vp, sz]),
+        "b200bls_g1_decompress_batch": (i32, [vp, vp, vp, sz]),
+        "b200bls_g2_decompress_batch": (i32, [vp, vp, vp, sz]),
+        "b200bls_g1_compress_batch": (i32, [vp, vp, sz]),
+        "b200bls_g2_compress_batch": (i32, [vp, vp, sz]),
+        "b200bls_hash_to_g2_batch": (i32, [vp, vp, sz]),
+        "b200bls_hash_to_g2_batch_dev": (i32, [vp, vp, sz]),
+        "b200bls_verify_batch": (i32, [vp, vp, vp, vp, sz]),
+        "b200bls_verify_batch_dev": (i32, [vp, vp, vp, vp, sz]),
+        "b200bls_aggregate_verify": (i32, [vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -63,6 +63,128 @@ def final_exp_batch(f):
     return out
 
 
+def miller_product(P, Q):
+    """prod_i miller(P_i, Q_i) as 576 bytes, NOT final-exponentiated (rank partial)"""
+    _lib.init()
+    P, Q, n = _pq(P, Q)
+    out = np.empty(576, dtype=np.uint8)
+    check(lib.b200bls_miller_product(ptr(P), ptr(Q), ptr(out), n))
+    return out
+
+
+def pairing_multi(P, Q):
+    """bls_py.pairing.ate_pairing_multi on byte buffers -> 576 bytes"""
+    _lib.init()
+    P, Q, n = _pq(P, Q)
+    out = np.empty(576, dtype=np.uint8)
+    check(lib.b200bls_pairing_multi(ptr(P), ptr(Q), ptr(out), n))
+    return out
+
+
+def _g(g2):
+    return ("g2", 192) if g2 else ("g1", 96)
+
+
+def scalar_mul(points, scalars, g2):
+    """n affine points x n 32-byte big-endian scalars -> n affine points"""
+    _lib.init()
+    name, w = _g(g2)
+    points, scalars = as_u8(points), as_u8(scalars)
+    n = points.size // w
+    if points.size != n * w or scalars.size != n * 32:
+        raise ValueError("bad buffer sizes")
+    out = np.empty(n * w, dtype=np.uint8)
+    check(getattr(lib, "b200bls_%s_scalar_mul_batch" % name)(ptr(points), ptr(scalars), ptr(out), n))
+    return out
+
+
+def point_add(a, b, g2):
+    _lib.init()
+    name, w = _g(g2)
+    a, b = as_u8(a), as_u8(b)
+    n = a.size // w
+    if a.size != n * w or b.size != a.size:
+        raise ValueError("bad buffer sizes")
+    out = np.empty(n * w, dtype=np.uint8)
+    check(getattr(lib, "b200bls_%s_add_batch" % name)(ptr(a), ptr(b), ptr(out), n))
+    return out
+
+
+def point_sum(points, g2):
+    """sum of n affine points -> one affine point (infinity = zero bytes)"""
+    _lib.init()
+    name, w = _g(g2)
+    points = as_u8(points)
+    n = points.size // w
+    if points.size != n * w:
+        raise ValueError("bad buffer size")
+    out = np.empty(w, dtype=np.uint8)
+    check(getattr(lib, "b200bls_%s_sum" % name)(ptr(points) if n else None, ptr(out), n))
+    return out
+
+
+def decompress(data, g2):
+    """compressed points -> (affine bytes, ok flags)"""
+    _lib.init()
+    name, w = _g(g2)
+    data = as_u8(data)
+    n = data.size // (w // 2)
+    if data.size != n * (w // 2):
+        raise ValueError("bad buffer size")
+    out = np.empty(n * w, dtype=np.uint8)
+    ok = np.empty(n, dtype=np.uint8)
+    check(getattr(lib, "b200bls_%s_decompress_batch" % name)(ptr(data), ptr(out), ptr(ok), n))
+    return out, ok
+
+
+def compress(points, g2):
+    _lib.init()
+    name, w = _g(g2)
+    points = as_u8(points)
+    n = points.size // w
+    if points.size != n * w:
+        raise ValueError("bad buffer size")
+    out = np.empty(n * (w // 2), dtype=np.uint8)
+    check(getattr(lib, "b200bls_%s_compress_batch" % name)(ptr(points), ptr(out), n))
+    return out
+
+
+def hash_to_g2(hashes):
+    """n x 32-byte message hashes -> n x 192 bytes (hash_to_point_prehashed_Fq2)"""
+    _lib.init()
+    hashes = as_u8(hashes)
+    n = hashes.size // 32
+    if hashes.size != n * 32:
+        raise ValueError("bad buffer size")
+    out = np.empty(n * 192, dtype=np.uint8)
+    check(lib.b200bls_hash_to_g2_batch(ptr(hashes), ptr(out), n))
+    return out
+
+
+def verify_batch(pks, hashes, sigs):
+    """n x (pk 96 B, message hash 32 B, sig 192 B) -> n result bytes"""
+    _lib.init()
+    pks, hashes, sigs = as_u8(pks), as_u8(hashes), as_u8(sigs)
+    n = hashes.size // 32
+    if pks.size != 96 * n or hashes.size != 32 * n or sigs.size != 192 * n:
+        raise ValueError("bad buffer sizes")
+    ok = np.empty(n, dtype=np.uint8)
+    check(lib.b200bls_verify_batch(ptr(pks), ptr(hashes), ptr(sigs), ptr(ok), n))
+    return ok
+
+
+def aggregate_verify(sig, pks, hashes):
+    """one aggregate signature (192 B affine) over n distinct message hashes -> bool"""
+    _lib.init()
+    sig, pks, hashes = as_u8(sig, 192), as_u8(pks), as_u8(hashes)
+    n = hashes.size // 32
+    if pks.size != 96 * n or hashes.size != 32 * n:
+        raise ValueError("bad buffer sizes")
+    ok = np.zeros(1, dtype=np.uint8)
+    check(lib.b200bls_aggregate_verify(ptr(sig), ptr(pks) if n else None, ptr(hashes) if n else None, n, ptr(ok)))
+    return bool(ok[0])
+
+
 class DeviceBuffer:
     """device memory owned by the library (for resident-data pipelines and benchmarks)"""
 

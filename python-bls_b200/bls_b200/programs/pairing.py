@@ -93,6 +93,39 @@ def miller_loop(prog, xp, yp, xq, yq):
     return f
 
 
+def miller_loop_multi(prog, pairs):
+    """product of Miller loops sharing the squarings of f.  pairs: list of
+    (xp, yp, xq, yq, inf) with inf a flag (or None): a pair flagged infinite contributes the
+    identity line (1, 0, 0) at every step, i.e. the factor 1 -- what the reference's blind
+    Miller loop on (0, 0) amounts to after the final exponentiation."""
+    one = prog.const2((1, 0))
+    zero = prog.const2((0, 0))
+
+    def guard(line, inf):
+        if inf is None:
+            return line
+        return (prog.sel2(inf, one, line[0]), prog.sel2(inf, zero, line[1]), prog.sel2(inf, zero, line[2]))
+
+    rs = [(xq, yq, one) for (_, _, xq, yq, _) in pairs]
+    f = None
+    for bit in X_BITS:
+        if f is not None:
+            f = f.sqr()
+        for k, (xp, yp, xq, yq, inf) in enumerate(pairs):
+            rs[k], line = double_step(prog, rs[k], xp, yp)
+            l0, l1, l4 = guard(line, inf)
+            if f is None:
+                f = F12(F6(l0, l1, zero), F6(zero, l4, zero))
+            else:
+                f = f.mul_by_014(l0, l1, l4)
+        if bit == "1":
+            for k, (xp, yp, xq, yq, inf) in enumerate(pairs):
+                rs[k], line = add_step(prog, rs[k], (xq, yq), xp, yp)
+                l0, l1, l4 = guard(line, inf)
+                f = f.mul_by_014(l0, l1, l4)
+    return f
+
+
 def _pow_bits(f, e, sqr):
     """f^e, MSB-first square and multiply"""
     acc = f
@@ -150,6 +183,103 @@ def build_pairing():
     e = final_exponentiation(prog, f)
     e = select_f12(prog, inf, f12_one(prog), e)
     store_f12(prog, BUF_OUT, e)
+    return prog
+
+
+NEG_G1 = (int("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac58"
+              "6c55e83ff97a1aeffb3af00adb22c6bb", 16),
+          Q - int("08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3ed"
+                  "d03cc744a2888ae40caa232946c5e7e1", 16))
+
+
+def f12_is_one(prog, f):
+    c = f.coeffs()
+    ok = c[0].eq(prog.const2((1, 0)))
+    for k in range(1, 6):
+        ok = ok & c[k].is_zero()
+    return ok
+
+
+def build_verify_pair():
+    """single-message verification core (bls_py/bls.py:194-201 with one message):
+        e(-G1, sig) * e(pk, H) == 1
+    buffers: 0 = pk (G1 affine, 96 B), 1 = H = hash_to_g2(message hash) (G2 affine, 192 B),
+    2 = sig (G2 affine, 192 B), 3 = result byte (1 = valid).  -G1 is the constant that the
+    reference recomputes as Fq(n, -1) * generator on every call (bls.py:197)."""
+    prog = Program("verify_pair")
+    prog.begin_body()
+    xk, yk = load_g1(prog, 0)
+    xh, yh = load_g2(prog, 1)
+    xs, ys = load_g2(prog, 2)
+    inf_pk = (xk.is_zero() & yk.is_zero()) | (xh.is_zero() & yh.is_zero())
+    inf_sig = xs.is_zero() & ys.is_zero()
+    ng = (prog.const1(NEG_G1[0]), prog.const1(NEG_G1[1]))
+    f = miller_loop_multi(prog, [(ng[0], ng[1], xs, ys, inf_sig), (xk, yk, xh, yh, inf_pk)])
+    e = final_exponentiation(prog, f)
+    prog.store_flag(3, 0, f12_is_one(prog, e))
+    return prog
+
+
+def build_miller_raw():
+    """Miller loop per item, written as Montgomery-form SoA (no byte conversion): stage 1 of
+    ate_pairing_multi (bls_py/fields_t.py:1114-1121).  buffers: 0 = P (n x 96),
+    1 = Q (n x 192), 2 = raw SoA Fq12 per item.  Infinite inputs contribute 1."""
+    prog = Program("miller_raw")
+    prog.begin_body()
+    xp, yp = load_g1(prog, BUF_P)
+    xq, yq = load_g2(prog, BUF_Q)
+    inf = (xp.is_zero() & yp.is_zero()) | (xq.is_zero() & yq.is_zero())
+    f = miller_loop_multi(prog, [(xp, yp, xq, yq, inf)])
+    for k, c in enumerate(f.coeffs()):
+        prog.store_raw2(2, k, c)
+    return prog
+
+
+def _f12_tree_product(prog, f, nt=128):
+    off = nt // 2
+    while off >= 1:
+        cs = f.coeffs()
+        prog.sync()
+        other = [prog.xmov2(c, off) for c in cs]
+        prog.sync()
+        f = f * F12.from_coeffs(other)
+        off //= 2
+    return f
+
+
+def _f12_strided_product(prog):
+    """prologue + body shared by the two product passes: every thread multiplies its strided
+    share of raw SoA Fq12 items (buffer 0) into a persistent accumulator"""
+    one12 = f12_one(prog)
+    acc = [prog.var2(c) for c in one12.coeffs()]
+    prog.begin_body()
+    act = prog.flag_active()
+    cs = [prog.load_raw2(0, k) for k in range(6)]
+    cs = [prog.sel2(act, c, o) for c, o in zip(cs, one12.coeffs())]
+    r = F12.from_coeffs(list(acc)) * F12.from_coeffs(cs)
+    for a, v in zip(acc, r.coeffs()):
+        prog.assign(a, v)
+    prog.begin_epilogue()
+    return _f12_tree_product(prog, F12.from_coeffs(list(acc)))
+
+
+def build_f12_product_pass1():
+    """stage 2 of ate_pairing_multi: buffers 0 = raw SoA Fq12 items, 1 = raw SoA partial
+    products, one per CTA (prod = fq12_mul(prod, ml_res), fields_t.py:1120, as a tree)."""
+    prog = Program("f12_prod1")
+    tot = _f12_strided_product(prog)
+    for k, c in enumerate(tot.coeffs()):
+        prog.store_raw2(1, k, c, block_only=True)
+    return prog
+
+
+def build_f12_product_pass2():
+    """stage 3: buffers 0 = raw SoA partials, 1 = their product as 576 big-endian bytes (NOT
+    final-exponentiated: this is the value ranks exchange in multi-GPU runs).  One CTA."""
+    prog = Program("f12_prod2")
+    tot = _f12_strided_product(prog)
+    for k, c in enumerate(tot.coeffs()):
+        prog.store2_be48(1, 96 * k, c, block_only=True)
     return prog
 
 

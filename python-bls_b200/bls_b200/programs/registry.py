@@ -1,5 +1,5 @@
 """Name -> builder table of every VM program embedded into libb200bls.so."""
-from . import fieldops, pairing
+from . import curve, fieldops, hashg2, pairing
 
 # Fq2 slots per thread.  One CTA of 128 threads per SM gets 18 slots (216 KB of shared memory);
 # two co-resident CTAs per SM get 9 slots each and hide each other's latencies.  Every program
@@ -15,3 +15,16 @@ PROGRAMS["fq2_mul_chain"] = fieldops.build_fq2_mul_chain(512)
 PROGRAMS["pairing"] = pairing.build_pairing
 PROGRAMS["miller_loop"] = pairing.build_miller_only
 PROGRAMS["final_exp"] = pairing.build_final_exp
+PROGRAMS["verify_pair"] = pairing.build_verify_pair
+PROGRAMS["miller_raw"] = pairing.build_miller_raw
+PROGRAMS["f12_prod1"] = pairing.build_f12_product_pass1
+PROGRAMS["f12_prod2"] = pairing.build_f12_product_pass2
+PROGRAMS["hash_to_g2"] = hashg2.build_hash_to_g2
+for _g2 in (False, True):
+    _p = "g2" if _g2 else "g1"
+    PROGRAMS[_p + "_mul"] = curve.build_scalar_mul(_g2)
+    PROGRAMS[_p + "_add"] = curve.build_add(_g2)
+    PROGRAMS[_p + "_sum1"] = curve.build_sum_pass1(_g2)
+    PROGRAMS[_p + "_sum2"] = curve.build_sum_pass2(_g2)
+    PROGRAMS[_p + "_decompress"] = curve.build_decompress(_g2)
+    PROGRAMS[_p + "_cflag"] = curve.build_compress_flag(_g2)

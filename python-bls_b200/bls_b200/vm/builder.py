@@ -248,16 +248,17 @@ class Program:
         return r
 
     # ---- I/O ----------------------------------------------------------------------------
-    def load1_be48(self, buf, off_bytes):
+    def load1_be48(self, buf, off_bytes, mask_top=False):
+        """mask_top: clear the three flag bits of byte 0 (buffer[0] & 0x1f, keys.py:31)"""
         assert off_bytes % 16 == 0
         r = V1(self)
-        self.emit("LDBE48", r, buf, off_bytes // 16)
+        self.emit("LDBE48", r, buf, off_bytes // 16, aux=int(mask_top))
         return r
 
-    def load2_be48(self, buf, off_bytes):
+    def load2_be48(self, buf, off_bytes, mask_top=False):
         """two consecutive 48-byte big-endian coefficients -> Fq2"""
         r = V2(self)
-        self.emit("LDBE48", Half(r, 0), buf, off_bytes // 16)
+        self.emit("LDBE48", Half(r, 0), buf, off_bytes // 16, aux=int(mask_top))
         self.emit("LDBE48", Half(r, 1), buf, off_bytes // 16 + 3)
         return r
 
@@ -267,15 +268,16 @@ class Program:
         self.emit("LDBE32", r, buf, off_bytes // 16)
         return r
 
-    def store1_be48(self, buf, off_bytes, v):
-        self.emit("STBE48", buf, v, off_bytes // 16)
+    # block_only=True: only thread 0 of the CTA stores, into the record of item = CTA index
+    def store1_be48(self, buf, off_bytes, v, block_only=False):
+        self.emit("STBE48", buf, v, off_bytes // 16, aux=int(block_only))
 
-    def store2_be48(self, buf, off_bytes, v):
-        self.emit("STBE48", buf, v.c0, off_bytes // 16)
-        self.emit("STBE48", buf, v.c1, off_bytes // 16 + 3)
+    def store2_be48(self, buf, off_bytes, v, block_only=False):
+        self.emit("STBE48", buf, v.c0, off_bytes // 16, aux=int(block_only))
+        self.emit("STBE48", buf, v.c1, off_bytes // 16 + 3, aux=int(block_only))
 
-    def store_flag(self, buf, off_bytes, f):
-        self.emit("STFLAG", buf, f, off_bytes)
+    def store_flag(self, buf, off_bytes, f, block_only=False):
+        self.emit("STFLAG", buf, f, off_bytes, aux=int(block_only))
 
     def load_raw2(self, buf, elem):
         r = V2(self)
@@ -449,7 +451,7 @@ def _assemble(prog, n_slots, n_cold):
         # evict the resident value with the farthest next use
         best, best_use = None, -1
         for vid in slot_of:
-            if vid in pinned or vid in fixed:
+            if vid in pinned or vid in fixed or vid in region_pins:
                 continue
             nu = next_use(vid, i - 1)
             if nu > best_use:
@@ -478,6 +480,7 @@ def _assemble(prog, n_slots, n_cold):
 
     marks = [None, None]
     skip_stack = []
+    region_pins = set()
     for i, op in enumerate(ops):
         if i == prog.section_marks["body"]:
             marks[0] = len(out)
@@ -487,7 +490,51 @@ def _assemble(prog, n_slots, n_cold):
             at = skip_stack.pop()
             w0, d, _, b = out[at]
             out[at] = (w0, d, len(out) - at - 1, b)
+            region_pins.clear()
             continue
+        if op.name == "SKIPZ":
+            # A skipped region must not contain spills or fills (they would be skipped too).
+            # Make every outside value it reads resident now, and free enough slots for the
+            # values it defines, before the branch.
+            end = i + 1
+            while ops[end].name != "SKIP_END":
+                end += 1
+            inside_defs, outside_used = [], []
+            for k in range(i + 1, end):
+                o = ops[k]
+                for x in (o.a, o.b):
+                    if _is_val(x) and not isinstance(root(x), Flag):
+                        vid = root(x).id
+                        if uses[vid][0] <= i and vid not in outside_used:
+                            outside_used.append(vid)
+                if _is_val(o.d) and not isinstance(root(o.d), Flag):
+                    vid = root(o.d).id
+                    if uses[vid][0] <= i:
+                        if vid not in outside_used:
+                            outside_used.append(vid)
+                    elif vid not in inside_defs:
+                        inside_defs.append(vid)
+            region_pins.update(outside_used)
+            for vid in outside_used:
+                if vid not in slot_of:
+                    sl = alloc_slot(i, region_pins)
+                    slot_of[vid] = sl
+                    emit("FILL2", 2 * sl, cold_of[vid])
+                    stats["fills"] += 1
+            # peak number of simultaneously live region-defined values
+            live, peak = set(), 0
+            for k in range(i + 1, end):
+                o = ops[k]
+                if _is_val(o.d) and not isinstance(root(o.d), Flag) and root(o.d).id in inside_defs:
+                    live.add(root(o.d).id)
+                    peak = max(peak, len(live))
+                for x in (o.a, o.b):
+                    if _is_val(x) and root(x).id in live and uses[root(x).id][-1] == k:
+                        live.discard(root(x).id)
+            held = []
+            while len(free_slots) + len(held) < peak + 1:
+                held.append(alloc_slot(i, region_pins))
+            free_slots.extend(held)
         fields = [op.d, op.a, op.b]
         srcs = [x for x in (op.a, op.b) if _is_val(x) and not isinstance(root(x), Flag)]
         # STBE48/STRAW2/SPILL-like ops read their 'a'; dst-position value operands that are

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/b200bls.h"
+#include "sha256.cuh"
 #include "vm_kernel.cuh"
 
 using namespace b200bls;
@@ -73,15 +74,19 @@ struct Context {
   uint4* cold = nullptr;
   size_t cold_bytes = 0;
   Staging staging[VM_MAX_BUFS];
+  Staging scratch[6];    // device-side intermediates of multi-stage entry points
   uint64_t launches = 0;
-  int ctas_per_sm = 1;   // 1: 18-slot programs, 2: the "#9" variants, two CTAs per SM
+  int ctas_per_sm = 2;   // 1: 18-slot programs, 2: the "#9" variants, two CTAs per SM
 };
 
 Context g_ctx;
 std::mutex g_mu;
 
-int ensure_staging(int i, size_t bytes) {
-  Staging& s = g_ctx.staging[i];
+int ensure_buf(Staging& s, size_t bytes);
+int ensure_staging(int i, size_t bytes) { return ensure_buf(g_ctx.staging[i], bytes); }
+int ensure_scratch(int i, size_t bytes) { return ensure_buf(g_ctx.scratch[i], bytes); }
+
+int ensure_buf(Staging& s, size_t bytes) {
   if (s.cap >= bytes) return 0;
   if (s.ptr) cudaFree(s.ptr);
   s.ptr = nullptr;
@@ -135,6 +140,7 @@ const DevProgram* find_program(const char* base) {
   std::string name(base);
   if (g_ctx.ctas_per_sm == 2 && name.find('#') == std::string::npos) name += "#9";
   auto it = g_ctx.programs.find(name);
+  if (it == g_ctx.programs.end()) it = g_ctx.programs.find(base);  // no 9-slot variant: 1 CTA/SM
   if (it == g_ctx.programs.end()) {
     fail(B200BLS_E_PROGRAM, "unknown program '%s'", name.c_str());
     return nullptr;
@@ -188,6 +194,165 @@ int run_dev(const char* name, size_t n, const DevBuf* db, int n_bufs) {
     bufs[i].stride = (long long)db[i].stride;
   }
   return launch_program(*pr, n, bufs, n_bufs);
+}
+
+
+int grid_for(const DevProgram& pr, size_t n_items) {
+  long long blocks_needed = (long long)((n_items + VM_NT - 1) / VM_NT);
+  long long max_grid = (long long)g_ctx.sm_count * (pr.n_slots <= 9 ? 2 : 1);
+  long long g = blocks_needed < max_grid ? blocks_needed : max_grid;
+  return g < 1 ? 1 : (int)g;
+}
+
+#define NEED_READY()                                                                       \
+  do {                                                                                     \
+    if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "b200bls_init() has not succeeded"); \
+  } while (0)
+
+int launch_named(const char* name, size_t n, const VmBuf* bufs, int n_bufs, int grid_override = 0) {
+  const DevProgram* pr = find_program(name);
+  if (!pr) return B200BLS_E_PROGRAM;
+  return launch_program(*pr, n, bufs, n_bufs, grid_override);
+}
+
+VmBuf vb(const void* p, long long stride) {
+  VmBuf b;
+  b.ptr = (unsigned char*)p;
+  b.stride = stride;
+  return b;
+}
+
+// ---- point sums: strided fold per thread + CTA tree (pass 1), then one CTA (pass 2) --------
+int sum_dev(bool g2, const void* pts, void* out, size_t n) {
+  NEED_READY();
+  const char* n1 = g2 ? "g2_sum1" : "g1_sum1";
+  const char* n2 = g2 ? "g2_sum2" : "g1_sum2";
+  size_t w = g2 ? 192 : 96;
+  if (n == 0) {  // empty sum = point at infinity = zero bytes
+    CU(cudaMemsetAsync(out, 0, w, g_ctx.stream));
+    return 0;
+  }
+  const DevProgram* p1 = find_program(n1);
+  if (!p1) return B200BLS_E_PROGRAM;
+  int grid = grid_for(*p1, n);
+  size_t raw_bytes = (size_t)(g2 ? 3 : 2) * 6 * sizeof(uint4) * grid;
+  int rc = ensure_scratch(0, raw_bytes);
+  if (rc) return rc;
+  VmBuf b1[2] = {vb(pts, (long long)w), vb(g_ctx.scratch[0].ptr, grid)};
+  rc = launch_program(*p1, n, b1, 2, grid);
+  if (rc) return rc;
+  VmBuf b2[2] = {vb(g_ctx.scratch[0].ptr, grid), vb(out, (long long)w)};
+  return launch_named(n2, (size_t)grid, b2, 2, 1);
+}
+
+// ---- multi-pairing: Miller loops -> raw Fq12 per item -> product tree ------------------------
+// out576: big-endian product of the Miller values (not final-exponentiated)
+int miller_product_dev(const void* P, const void* Q, void* out576, size_t n) {
+  NEED_READY();
+  if (n == 0) return fail(B200BLS_E_ARG, "pairing_multi needs at least one pair");
+  int rc = ensure_scratch(1, (size_t)576 * n);
+  if (rc) return rc;
+  VmBuf ba[3] = {vb(P, 96), vb(Q, 192), vb(g_ctx.scratch[1].ptr, (long long)n)};
+  rc = launch_named("miller_raw", n, ba, 3);
+  if (rc) return rc;
+  const DevProgram* p1 = find_program("f12_prod1");
+  if (!p1) return B200BLS_E_PROGRAM;
+  int grid = grid_for(*p1, n);
+  rc = ensure_scratch(2, (size_t)576 * grid);
+  if (rc) return rc;
+  VmBuf bb[2] = {vb(g_ctx.scratch[1].ptr, (long long)n), vb(g_ctx.scratch[2].ptr, grid)};
+  rc = launch_program(*p1, n, bb, 2, grid);
+  if (rc) return rc;
+  VmBuf bc[2] = {vb(g_ctx.scratch[2].ptr, grid), vb(out576, 576)};
+  return launch_named("f12_prod2", (size_t)grid, bc, 2, 1);
+}
+
+int sha_stage_dev(const void* hashes, void* out256, size_t n) {
+  long long threads = (long long)n * 8;
+  int block = 256;
+  long long grid = (threads + block - 1) / block;
+  sha_stage_kernel<<<(unsigned)grid, block, 0, g_ctx.stream>>>((const uint8_t*)hashes, (uint8_t*)out256, (long long)n);
+  CU(cudaGetLastError());
+  g_ctx.launches++;
+  return 0;
+}
+
+int hash_to_g2_dev(const void* hashes, void* out, size_t n) {
+  NEED_READY();
+  if (n == 0) return 0;
+  int rc = ensure_scratch(3, (size_t)256 * n);
+  if (rc) return rc;
+  rc = sha_stage_dev(hashes, g_ctx.scratch[3].ptr, n);
+  if (rc) return rc;
+  VmBuf b[2] = {vb(g_ctx.scratch[3].ptr, 256), vb(out, 192)};
+  return launch_named("hash_to_g2", n, b, 2);
+}
+
+int verify_dev(const void* pk, const void* mh, const void* sig, void* ok, size_t n) {
+  NEED_READY();
+  if (n == 0) return 0;
+  int rc = ensure_scratch(4, (size_t)192 * n);
+  if (rc) return rc;
+  rc = hash_to_g2_dev(mh, g_ctx.scratch[4].ptr, n);
+  if (rc) return rc;
+  VmBuf b[4] = {vb(pk, 96), vb(g_ctx.scratch[4].ptr, 192), vb(sig, 192), vb(ok, 1)};
+  return launch_named("verify_pair", n, b, 4);
+}
+
+// x bytes of each affine point with (flag << 7) OR-ed into byte 0 (bls_py/ec.py:103-111)
+__global__ void compress_pack_kernel(const uint8_t* __restrict__ aff, const uint8_t* __restrict__ flag,
+                                     uint8_t* __restrict__ out, long long n, int xbytes) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long words = (long long)xbytes / 4;
+  if (t >= n * words) return;
+  long long item = t / words;
+  int wi = (int)(t % words);
+  uint32_t v = reinterpret_cast<const uint32_t*>(aff + item * 2 * xbytes)[wi];
+  if (wi == 0 && flag[item]) v |= 0x80u;  // byte 0 is the low byte of the first little-endian word
+  reinterpret_cast<uint32_t*>(out + item * xbytes)[wi] = v;
+}
+
+int compress_dev(bool g2, const void* aff, void* out, size_t n) {
+  NEED_READY();
+  if (n == 0) return 0;
+  int rc = ensure_scratch(5, n);
+  if (rc) return rc;
+  int xb = g2 ? 96 : 48;
+  VmBuf b[2] = {vb(aff, 2 * xb), vb(g_ctx.scratch[5].ptr, 1)};
+  rc = launch_named(g2 ? "g2_cflag" : "g1_cflag", n, b, 2);
+  if (rc) return rc;
+  long long threads = (long long)n * (xb / 4);
+  compress_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, g_ctx.stream>>>(
+      (const uint8_t*)aff, (const uint8_t*)g_ctx.scratch[5].ptr, (uint8_t*)out, (long long)n, xb);
+  CU(cudaGetLastError());
+  g_ctx.launches++;
+  return 0;
+}
+
+// host-pointer wrapper around a device pipeline: ins/outs are (host ptr, bytes) pairs staged
+// through g_ctx.staging[0..]
+struct HostIO {
+  const void* in;
+  void* out;
+  size_t bytes;
+};
+
+template <class F>
+int with_staging(const HostIO* io, int n_io, F&& body) {
+  NEED_READY();
+  void* dev[VM_MAX_BUFS];
+  for (int i = 0; i < n_io; i++) {
+    int rc = ensure_staging(i, io[i].bytes ? io[i].bytes : 1);
+    if (rc) return rc;
+    dev[i] = g_ctx.staging[i].ptr;
+    if (io[i].in && io[i].bytes) CU(cudaMemcpyAsync(dev[i], io[i].in, io[i].bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+  }
+  int rc = body(dev);
+  if (rc) return rc;
+  for (int i = 0; i < n_io; i++)
+    if (io[i].out && io[i].bytes) CU(cudaMemcpyAsync(io[i].out, dev[i], io[i].bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+  CU(cudaStreamSynchronize(g_ctx.stream));
+  return 0;
 }
 
 const char* kFieldOps[] = {"add", "sub", "mul", "sqr", "neg", "inv"};
@@ -270,6 +435,11 @@ void b200bls_shutdown(void) {
   }
   c.programs.clear();
   for (auto& s : c.staging) {
+    if (s.ptr) cudaFree(s.ptr);
+    s.ptr = nullptr;
+    s.cap = 0;
+  }
+  for (auto& s : c.scratch) {
     if (s.ptr) cudaFree(s.ptr);
     s.ptr = nullptr;
     s.cap = 0;
@@ -445,6 +615,183 @@ int b200bls_miller_loop_batch_dev(const void* P, const void* Q, void* out, size_
   std::lock_guard<std::mutex> lk(g_mu);
   DevBuf db[3] = {{P, 96}, {Q, 192}, {out, 576}};
   return run_dev("miller_loop", n, db, 3);
+}
+
+
+// ---- curve ---------------------------------------------------------------------------------
+int b200bls_g1_scalar_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!pts || !scalars || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[3] = {{pts, nullptr, 96}, {scalars, nullptr, 32}, {nullptr, out, 96}};
+  return run_host("g1_mul", n, hb, 3);
+}
+int b200bls_g1_scalar_mul_batch_dev(const void* pts, const void* scalars, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  DevBuf db[3] = {{pts, 96}, {scalars, 32}, {out, 96}};
+  return run_dev("g1_mul", n, db, 3);
+}
+int b200bls_g2_scalar_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!pts || !scalars || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[3] = {{pts, nullptr, 192}, {scalars, nullptr, 32}, {nullptr, out, 192}};
+  return run_host("g2_mul", n, hb, 3);
+}
+int b200bls_g2_scalar_mul_batch_dev(const void* pts, const void* scalars, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  DevBuf db[3] = {{pts, 192}, {scalars, 32}, {out, 192}};
+  return run_dev("g2_mul", n, db, 3);
+}
+int b200bls_g1_add_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!a || !b || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[3] = {{a, nullptr, 96}, {b, nullptr, 96}, {nullptr, out, 96}};
+  return run_host("g1_add", n, hb, 3);
+}
+int b200bls_g2_add_batch(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!a || !b || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[3] = {{a, nullptr, 192}, {b, nullptr, 192}, {nullptr, out, 192}};
+  return run_host("g2_add", n, hb, 3);
+}
+int b200bls_g1_sum_dev(const void* pts, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return sum_dev(false, pts, out, n);
+}
+int b200bls_g2_sum_dev(const void* pts, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return sum_dev(true, pts, out, n);
+}
+int b200bls_g1_sum(const uint8_t* pts, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out || (n && !pts)) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[2] = {{pts, nullptr, 96 * n}, {nullptr, out, 96}};
+  return with_staging(io, 2, [&](void** d) { return sum_dev(false, d[0], d[1], n); });
+}
+int b200bls_g2_sum(const uint8_t* pts, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out || (n && !pts)) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[2] = {{pts, nullptr, 192 * n}, {nullptr, out, 192}};
+  return with_staging(io, 2, [&](void** d) { return sum_dev(true, d[0], d[1], n); });
+}
+int b200bls_g1_decompress_batch(const uint8_t* in, uint8_t* out, uint8_t* ok, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!in || !out || !ok) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[3] = {{in, nullptr, 48}, {nullptr, out, 96}, {nullptr, ok, 1}};
+  return run_host("g1_decompress", n, hb, 3);
+}
+int b200bls_g2_decompress_batch(const uint8_t* in, uint8_t* out, uint8_t* ok, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!in || !out || !ok) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[3] = {{in, nullptr, 96}, {nullptr, out, 192}, {nullptr, ok, 1}};
+  return run_host("g2_decompress", n, hb, 3);
+}
+int b200bls_g1_compress_batch(const uint8_t* in, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!in || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[2] = {{in, nullptr, 96 * n}, {nullptr, out, 48 * n}};
+  return with_staging(io, 2, [&](void** d) { return compress_dev(false, d[0], d[1], n); });
+}
+int b200bls_g2_compress_batch(const uint8_t* in, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!in || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[2] = {{in, nullptr, 192 * n}, {nullptr, out, 96 * n}};
+  return with_staging(io, 2, [&](void** d) { return compress_dev(true, d[0], d[1], n); });
+}
+
+// ---- hashing, multi-pairing, verification ----------------------------------------------------
+int b200bls_hash_to_g2_batch(const uint8_t* hashes, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!hashes || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[2] = {{hashes, nullptr, 32 * n}, {nullptr, out, 192 * n}};
+  return with_staging(io, 2, [&](void** d) { return hash_to_g2_dev(d[0], d[1], n); });
+}
+int b200bls_hash_to_g2_batch_dev(const void* hashes, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return hash_to_g2_dev(hashes, out, n);
+}
+int b200bls_miller_product(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!P || !Q || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[3] = {{P, nullptr, 96 * n}, {Q, nullptr, 192 * n}, {nullptr, out, 576}};
+  return with_staging(io, 3, [&](void** d) { return miller_product_dev(d[0], d[1], d[2], n); });
+}
+int b200bls_miller_product_dev(const void* P, const void* Q, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return miller_product_dev(P, Q, out, n);
+}
+int b200bls_pairing_multi(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!P || !Q || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[4] = {{P, nullptr, 96 * n}, {Q, nullptr, 192 * n}, {nullptr, nullptr, 576}, {nullptr, out, 576}};
+  return with_staging(io, 4, [&](void** d) {
+    int rc = miller_product_dev(d[0], d[1], d[2], n);
+    if (rc) return rc;
+    VmBuf b[2] = {vb(d[2], 576), vb(d[3], 576)};
+    return launch_named("final_exp", 1, b, 2);
+  });
+}
+int b200bls_pairing_multi_dev(const void* P, const void* Q, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_READY();
+  int rc = ensure_scratch(5, 576);
+  if (rc) return rc;
+  rc = miller_product_dev(P, Q, g_ctx.scratch[5].ptr, n);
+  if (rc) return rc;
+  VmBuf b[2] = {vb(g_ctx.scratch[5].ptr, 576), vb(out, 576)};
+  return launch_named("final_exp", 1, b, 2);
+}
+int b200bls_verify_batch(const uint8_t* pk, const uint8_t* mh, const uint8_t* sig, uint8_t* ok, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!pk || !mh || !sig || !ok) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[4] = {{pk, nullptr, 96 * n}, {mh, nullptr, 32 * n}, {sig, nullptr, 192 * n}, {nullptr, ok, n}};
+  return with_staging(io, 4, [&](void** d) { return verify_dev(d[0], d[1], d[2], d[3], n); });
+}
+int b200bls_verify_batch_dev(const void* pk, const void* mh, const void* sig, void* ok, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return verify_dev(pk, mh, sig, ok, n);
+}
+
+
+// e(-G1, sig) * prod_i e(pk_i, H(mh_i)) == 1 for distinct message hashes and unit exponents:
+// the core of BLS.verify (bls_py/bls.py:194-201) after its host-side grouping
+int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_READY();
+  if (!sig || !ok || (n && (!pks || !mhs))) return fail(B200BLS_E_ARG, "null buffer");
+  static const uint8_t kNegG1[96] = {
+      0x17, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f,
+      0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05, 0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58,
+      0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb,
+      0x11, 0x4d, 0x1d, 0x68, 0x55, 0xd5, 0x45, 0xa8, 0xaa, 0x7d, 0x76, 0xc8, 0xcf, 0x2e, 0x21, 0xf2,
+      0x67, 0x81, 0x6a, 0xef, 0x1d, 0xb5, 0x07, 0xc9, 0x66, 0x55, 0xb9, 0xd5, 0xca, 0xac, 0x42, 0x36,
+      0x4e, 0x6f, 0x38, 0xba, 0x0e, 0xcb, 0x75, 0x1b, 0xad, 0x54, 0xdc, 0xd6, 0xb9, 0x39, 0xc2, 0xca};
+  int rc;
+  if ((rc = ensure_staging(0, 96 * (n + 1)))) return rc;
+  if ((rc = ensure_staging(1, 32 * n + 1))) return rc;
+  if ((rc = ensure_staging(2, 192 * (n + 1)))) return rc;
+  if ((rc = ensure_staging(3, 576 * 2))) return rc;
+  uint8_t* dP = (uint8_t*)g_ctx.staging[0].ptr;
+  uint8_t* dM = (uint8_t*)g_ctx.staging[1].ptr;
+  uint8_t* dQ = (uint8_t*)g_ctx.staging[2].ptr;
+  uint8_t* dF = (uint8_t*)g_ctx.staging[3].ptr;
+  CU(cudaMemcpyAsync(dP, kNegG1, 96, cudaMemcpyHostToDevice, g_ctx.stream));
+  CU(cudaMemcpyAsync(dQ, sig, 192, cudaMemcpyHostToDevice, g_ctx.stream));
+  if (n) {
+    CU(cudaMemcpyAsync(dP + 96, pks, 96 * n, cudaMemcpyHostToDevice, g_ctx.stream));
+    CU(cudaMemcpyAsync(dM, mhs, 32 * n, cudaMemcpyHostToDevice, g_ctx.stream));
+    if ((rc = hash_to_g2_dev(dM, dQ + 192, n))) return rc;
+  }
+  if ((rc = miller_product_dev(dP, dQ, dF, n + 1))) return rc;
+  VmBuf b[2] = {vb(dF, 576), vb(dF + 576, 576)};
+  if ((rc = launch_named("final_exp", 1, b, 2))) return rc;
+  uint8_t res[576];
+  CU(cudaMemcpyAsync(res, dF + 576, 576, cudaMemcpyDeviceToHost, g_ctx.stream));
+  CU(cudaStreamSynchronize(g_ctx.stream));
+  bool one = res[47] == 1;
+  for (int i = 0; i < 576 && one; i++)
+    if (i != 47 && res[i] != 0) one = false;
+  *ok = one ? 1 : 0;
+  return 0;
 }
 
 }  // extern "C"

@@ -96,8 +96,13 @@ struct DevEnv {
   __device__ __forceinline__ uint32_t ld_byte(int buf, int off) {
     return p->bufs[buf].ptr[item * p->bufs[buf].stride + off];
   }
-  __device__ __forceinline__ void st_byte(int buf, int off, unsigned char v) {
-    if (active()) p->bufs[buf].ptr[item * p->bufs[buf].stride + off] = v;
+  // block_only: thread 0 of the CTA writes the record of item = CTA index (reduction results)
+  __device__ __forceinline__ void st_byte(int buf, int off, unsigned char v, bool block_only) {
+    if (block_only) {
+      if (threadIdx.x == 0) p->bufs[buf].ptr[(long long)blockIdx.x * p->bufs[buf].stride + off] = v;
+    } else if (active()) {
+      p->bufs[buf].ptr[item * p->bufs[buf].stride + off] = v;
+    }
   }
   __device__ __forceinline__ void ld_be(int buf, int off, int nwords, fp& x) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p->bufs[buf].ptr + item * p->bufs[buf].stride + off);
@@ -111,9 +116,15 @@ struct DevEnv {
       for (int i = 0; i < 8; i++) x.v[i] = __byte_perm(__ldg(w + 7 - i), 0, 0x0123);
     }
   }
-  __device__ __forceinline__ void st_be48(int buf, int off, const fp& x) {
-    if (!active()) return;
-    uint32_t* w = reinterpret_cast<uint32_t*>(p->bufs[buf].ptr + item * p->bufs[buf].stride + off);
+  __device__ __forceinline__ void st_be48(int buf, int off, const fp& x, bool block_only) {
+    long long it = item;
+    if (block_only) {
+      if (threadIdx.x != 0) return;
+      it = blockIdx.x;
+    } else if (!active()) {
+      return;
+    }
+    uint32_t* w = reinterpret_cast<uint32_t*>(p->bufs[buf].ptr + it * p->bufs[buf].stride + off);
 #pragma unroll
     for (int i = 0; i < NL; i++) w[11 - i] = __byte_perm(x.v[i], 0, 0x0123);
   }

@@ -53,8 +53,12 @@ struct HostEnv {
   bool any_flag(int f) { return true; }  // hostsim never skips: SKIPZ is an optimisation only
   bool active() { return item_raw < sh->n_items; }
   uint32_t ld_byte(int buf, int off) { return sh->bufs[buf][item * sh->strides[buf] + off]; }
-  void st_byte(int buf, int off, uint8_t v) {
-    if (active()) sh->bufs[buf][item * sh->strides[buf] + off] = v;
+  void st_byte(int buf, int off, uint8_t v, bool block_only) {
+    if (block_only) {
+      if (tid == 0) sh->bufs[buf][blk * sh->strides[buf] + off] = v;
+    } else if (active()) {
+      sh->bufs[buf][item * sh->strides[buf] + off] = v;
+    }
   }
   void ld_be(int buf, int off, int nwords, fp& x) {
     const uint8_t* p = sh->bufs[buf] + item * sh->strides[buf] + off;
@@ -65,9 +69,15 @@ struct HostEnv {
       x.v[i] = __builtin_bswap32(w);
     }
   }
-  void st_be48(int buf, int off, const fp& x) {
-    if (!active()) return;
-    uint8_t* p = sh->bufs[buf] + item * sh->strides[buf] + off;
+  void st_be48(int buf, int off, const fp& x, bool block_only) {
+    long it = item;
+    if (block_only) {
+      if (tid != 0) return;
+      it = blk;
+    } else if (!active()) {
+      return;
+    }
+    uint8_t* p = sh->bufs[buf] + it * sh->strides[buf] + off;
     for (int i = 0; i < NL; i++) {
       uint32_t w = __builtin_bswap32(x.v[i]);
       memcpy(p + 4 * (NL - 1 - i), &w, 4);

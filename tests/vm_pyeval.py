@@ -122,16 +122,25 @@ def run(prog, bufs, n_items, n_threads=1, strides=None, out_bufs=None):
                     f = get(st, op.aux)
                     r = (list(a) if nm == "CSEL2" else a) if f else (list(b) if nm == "CSEL2" else b)
                 elif nm == "LDBE48":
-                    r = rd(op.a, item, 16 * op.b, 48) % Q
+                    r = rd(op.a, item, 16 * op.b, 48)
+                    if op.aux:
+                        r &= (1 << 381) - 1
+                    r %= Q
                 elif nm == "LDBE32":
                     r = rd(op.a, item, 16 * op.b, 32) % Q
                 elif nm == "STBE48":
-                    if active:
+                    if op.aux:
+                        if t == 0:
+                            bufs[op.d][16 * op.b:16 * op.b + 48] = int(a).to_bytes(48, "big")
+                    elif active:
                         base = item * strides.get(op.d, 0) + 16 * op.b
                         bufs[op.d][base:base + 48] = int(a).to_bytes(48, "big")
                     continue
                 elif nm == "STFLAG":
-                    if active:
+                    if op.aux:
+                        if t == 0:
+                            bufs[op.d][op.b] = 1 if a else 0
+                    elif active:
                         bufs[op.d][item * strides.get(op.d, 0) + op.b] = 1 if a else 0
                     continue
                 elif nm == "LDRAW2":
