@@ -1,0 +1,157 @@
+"""Curve points of the scheme layer, backed by the GPU engine.
+
+The reference keeps points as Python objects over Fq/Fq2 ints and does every operation in
+the interpreter (bls_py/ec.py:18-391).  Here a point is its canonical affine byte string
+(96 bytes for G1, 192 for G2, zero bytes for infinity -- the reference's own
+(0, 0, infinity=True) affine form, fields_t.py:609-622) and every operator is one call into
+the batched C ABI.  Serialisation is byte-identical (ec.py:94-111)."""
+import numpy as np
+
+from . import engine
+from .programs.curve import G1_GEN
+from .programs.hashg2 import G2_GEN
+from .util import hash256
+
+Q = int("1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f624"
+        "1eabfffeb153ffffb9feffffffffaaab", 16)
+N = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+
+class Point:
+    """affine point on E(Fq) (g2=False) or on the twist E'(Fq2) (g2=True)"""
+    __slots__ = ("raw", "g2", "_ser")
+
+    def __init__(self, raw, g2):
+        raw = bytes(raw)
+        if len(raw) != (192 if g2 else 96):
+            raise ValueError("bad point encoding length %d" % len(raw))
+        self.raw = raw
+        self.g2 = g2
+        self._ser = None
+
+    # -- reference-style accessors --------------------------------------------------------
+    @property
+    def infinity(self):
+        return not any(self.raw)
+
+    @property
+    def x(self):
+        c = [int.from_bytes(self.raw[i:i + 48], "big") for i in range(0, len(self.raw) // 2, 48)]
+        return tuple(c) if self.g2 else c[0]
+
+    @property
+    def y(self):
+        h = len(self.raw) // 2
+        c = [int.from_bytes(self.raw[i:i + 48], "big") for i in range(h, 2 * h, 48)]
+        return tuple(c) if self.g2 else c[0]
+
+    def to_affine(self):
+        return self
+
+    def to_jacobian(self):
+        return self
+
+    # -- arithmetic (one GPU call each; use bls_b200.engine for batches) ----------------------
+    def __add__(self, other):
+        if other == 0 and not isinstance(other, Point):
+            return self
+        if not isinstance(other, Point) or other.g2 != self.g2:
+            raise TypeError("cannot add %r" % type(other))
+        return Point(engine.point_add(self.raw, other.raw, self.g2).tobytes(), self.g2)
+
+    __radd__ = __add__
+
+    def negate(self):
+        if self.infinity:
+            return self
+        h = len(self.raw) // 2
+        y = [(-int.from_bytes(self.raw[i:i + 48], "big")) % Q for i in range(h, 2 * h, 48)]
+        return Point(self.raw[:h] + b"".join(v.to_bytes(48, "big") for v in y), self.g2)
+
+    def __neg__(self):
+        return self.negate()
+
+    def __sub__(self, other):
+        return self + other.negate()
+
+    def __mul__(self, k):
+        k = int(k)
+        if k < 0 or k >> 256:
+            k %= N                      # valid for points of order n (every public object here)
+        return Point(engine.scalar_mul(self.raw, k.to_bytes(32, "big"), self.g2).tobytes(), self.g2)
+
+    __rmul__ = __mul__
+
+    def __eq__(self, other):
+        return isinstance(other, Point) and self.g2 == other.g2 and self.raw == other.raw
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash((self.g2, self.raw))
+
+    def serialize(self):
+        """x with the 'y is the larger root' flag in the top bit (ec.py:94-111)"""
+        if self._ser is None:
+            self._ser = engine.compress(self.raw, self.g2).tobytes()
+        return self._ser
+
+    def __repr__(self):
+        return "%s(%s)" % ("G2" if self.g2 else "G1", self.serialize().hex())
+
+
+# the reference exposes both coordinate systems; here they are one class
+AffinePoint = JacobianPoint = Point
+
+
+def generator_Fq():
+    return Point(b"".join(c.to_bytes(48, "big") for c in G1_GEN), False)
+
+
+def generator_Fq2():
+    return Point(b"".join(c.to_bytes(48, "big") for c in (G2_GEN[0] + G2_GEN[1])), True)
+
+
+def infinity(g2):
+    return Point(bytes(192 if g2 else 96), g2)
+
+
+def point_from_bytes(data, g2):
+    """PublicKey.from_bytes / Signature.from_bytes decoding (keys.py:29-40, signature.py:22-38);
+    raises ValueError where the reference does"""
+    out, ok = engine.decompress(data, g2)
+    if not ok[0]:
+        raise ValueError("No y for point x")
+    return Point(out.tobytes(), g2)
+
+
+def hash_to_point_prehashed_Fq2(h):
+    """ec.py:528-550"""
+    if not isinstance(h, (bytes, bytearray)):
+        h = h.encode("utf-8")
+    if len(h) != 32:
+        raise ValueError("the batched hash-to-G2 takes 32-byte message hashes")
+    return Point(engine.hash_to_g2(bytes(h)).tobytes(), True)
+
+
+def hash_to_point_Fq2(m):
+    """ec.py:553-555"""
+    return hash_to_point_prehashed_Fq2(hash256(m))
+
+
+def sum_points(points, g2):
+    """sum of many points in one reduction on the GPU"""
+    if not points:
+        return infinity(g2)
+    return Point(engine.point_sum(b"".join(p.raw for p in points), g2).tobytes(), g2)
+
+
+def scalar_mul_many(points, scalars, g2):
+    """[k_i * P_i] in one batched call"""
+    if not points:
+        return []
+    w = 192 if g2 else 96
+    sc = b"".join((int(k) % (1 << 256) if int(k) >= 0 else int(k) % N).to_bytes(32, "big") for k in scalars)
+    out = engine.scalar_mul(b"".join(p.raw for p in points), sc, g2).tobytes()
+    return [Point(out[w * i:w * (i + 1)], g2) for i in range(len(points))]

@@ -1,0 +1,74 @@
+"""CPU tests of the host-side scheme logic (no GPU needed): hashing helpers, aggregation
+exponents and AggregationInfo merging against vectors generated from the live reference."""
+import bls_oracle as O
+from conftest import load_golden
+
+from bls_b200 import ec, synth
+from bls_b200.aggregation_info import AggregationInfo
+from bls_b200.keys import PublicKey
+from bls_b200.util import hash256, hash512, hash_pks, hmac256
+
+
+def stub_pk(ser_hex):
+    """a PublicKey whose serialisation is preset, so no GPU call is needed"""
+    p = ec.Point(bytes(96), False)
+    p._ser = bytes.fromhex(ser_hex)
+    return PublicKey(p)
+
+
+def test_hash_helpers_match_oracle():
+    for m in (b"", b"abc", bytes(range(200))):
+        assert hash256(m) == O.hash256(m)
+        assert hash512(m) == O.hash512(m)
+        assert hmac256(m, b"BLS private key seed") == O.hmac256(m, b"BLS private key seed")
+    assert hmac256(b"x", bytes(100)) == O.hmac256(b"x", bytes(100))      # long key is hashed first
+
+
+def test_private_key_from_seed_vector():
+    from bls_b200.keys import PrivateKey
+    g = load_golden("sig_kat.json")
+    for k in g["keys"]:
+        assert PrivateKey.from_seed(bytes.fromhex(k["seed"])).serialize().hex() == k["sk"]
+
+
+def test_hash_pks_matches_oracle():
+    g = load_golden("sig_kat.json")
+    pks = [stub_pk(k["pk"]) for k in g["keys"]]
+    assert hash_pks(3, pks) == O.hash_pks(3, [bytes.fromhex(k["pk"]) for k in g["keys"]])
+
+
+def test_merge_infos_reproduces_reference_tree():
+    """tests.py:150-172: sig_final = agg([agg([s1, s2]), agg([s3, s4, s5]), s6])"""
+    g = load_golden("sig_kat.json")
+    pk1, pk2 = [stub_pk(k["pk"]) for k in g["keys"]]
+    m1, m2, m3, m4 = [hash256(bytes(m)) for m in ([1, 2, 3, 40], [5, 6, 70, 201], [9, 10, 11, 12, 13],
+                                                  [15, 63, 244, 92, 0, 1])]
+    i1, i2, i3 = (AggregationInfo.from_msg_hash(pk1, m1), AggregationInfo.from_msg_hash(pk2, m2),
+                  AggregationInfo.from_msg_hash(pk2, m1))
+    i4, i5, i6 = (AggregationInfo.from_msg_hash(pk1, m3), AggregationInfo.from_msg_hash(pk1, m1),
+                  AggregationInfo.from_msg_hash(pk1, m4))
+    left = AggregationInfo.merge_infos([i1, i2])
+    right = AggregationInfo.merge_infos([i3, i4, i5])
+    final = AggregationInfo.merge_infos([left, right, i6])
+    got = sorted([k[0].hex(), k[1].serialize().hex(), hex(e)] for k, e in final.tree.items())
+    assert got == g["test_vectors2"]["final_tree"]
+    assert final.message_hashes == sorted(final.message_hashes) or len(set(final.message_hashes)) < len(final.message_hashes)
+    assert [(mh, pk) for mh, pk in zip(final.message_hashes, final.public_keys)] == sorted(final.tree.keys())
+
+
+def test_aggregation_info_ordering():
+    pk1, pk2 = stub_pk("00" * 47 + "01"), stub_pk("00" * 47 + "02")
+    a = AggregationInfo.from_msg_hash(pk1, b"\x01" * 32)
+    b = AggregationInfo.from_msg_hash(pk2, b"\x01" * 32)
+    c = AggregationInfo.merge_infos([a, AggregationInfo.from_msg_hash(pk2, b"\x02" * 32)])
+    assert a < b and not b < a and a == a.copy()
+    assert a < c                                  # a proper prefix sorts first
+    assert sorted([b, c, a])[0] is a
+
+
+def test_synthetic_inputs_are_reproducible():
+    s = synth.scalars(synth.SEED_PAIRING, 5)
+    assert s.shape == (5, 32) and (s[:, 0] < 0x40).all()
+    assert (synth.scalars(synth.SEED_PAIRING, 5) == s).all()
+    bad = synth.corrupted_indices(7, 1000)
+    assert len(bad) == 10 and len(set(bad.tolist())) == 10

@@ -1,0 +1,24 @@
+#!/usr/bin/env python3
+"""Small fixed workload for ncu: three launches of the pairing program over one full wave
+(2 CTAs x 128 threads per SM), inputs resident on the device."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "python-bls_b200"))
+from bls_b200 import _lib, engine                           # noqa: E402
+
+_lib.init(0)
+n = _lib.lib.b200bls_sm_count() * 256
+rng = np.random.default_rng(7)
+P = rng.integers(0, 256, size=(n, 96), dtype=np.uint8)
+Q = rng.integers(0, 256, size=(n, 192), dtype=np.uint8)
+P[:, ::48] &= 0x0f
+Q[:, ::48] &= 0x0f
+dP, dQ, dO = engine.DeviceBuffer(96 * n).upload(P), engine.DeviceBuffer(192 * n).upload(Q), engine.DeviceBuffer(576 * n)
+for _ in range(3):
+    engine.timer_start()
+    _lib.check(_lib.lib.b200bls_pairing_batch_dev(dP.ptr, dQ.ptr, dO.ptr, n))
+    print("pairing n=%d: %.3f ms" % (n, engine.timer_stop()))
