@@ -178,8 +178,11 @@ def run_gpu(args, rank, world, dist):
         p2, q2 = engine.DeviceBuffer(96 * n).upload(hP), engine.DeviceBuffer(192 * n).upload(hQ)
         sets.append((p2, q2, engine.DeviceBuffer(576 * n)))
 
+    N_STREAMS = 2        # consecutive batches go to alternating library streams and overlap
+
     def step(i):
         p, q, o = sets[i % NSETS]
+        check(lib.b200bls_set_stream(i % N_STREAMS))
         check(lib.b200bls_pairing_batch_dev(p.ptr, q.ptr, o.ptr, n))
 
     def barrier():
@@ -203,6 +206,7 @@ def run_gpu(args, rank, world, dist):
     launches = lib.b200bls_launch_count() - launches0
     barrier()
     clocks = sampler.stop()
+    check(lib.b200bls_set_stream(0))
 
     # --- end to end through the host-buffer C ABI call, pinned host memory
     def pinned(nbytes):
@@ -277,7 +281,7 @@ def run_gpu(args, rank, world, dist):
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Montgomery)",
         "data": "synthetic", "gpu_launches": int(launches),
         "config": {"workload": WORKLOAD, "batch_per_gpu": n, "l2": "inputs rotate over %d buffer sets (%d MB > L2)"
-                   % (NSETS, NSETS * hbm_bytes // 2 ** 20), "ctas_per_sm": lib.b200bls_get_ctas_per_sm(),
+                   % (NSETS, NSETS * hbm_bytes // 2 ** 20), "ctas_per_sm": lib.b200bls_get_ctas_per_sm(), "streams": N_STREAMS,
                    "parity_spot_check": parity},
         "e2e": {"value": e2e, "unit": METRIC, "h2d_bytes_per_step": n * 288, "d2h_bytes_per_step": n * 576,
                 "steps": e2e_steps, "api": "b200bls_pairing_batch (host buffers, pinned)"},

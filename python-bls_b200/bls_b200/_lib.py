@@ -27,6 +27,8 @@ def _load():
         "b200bls_last_error": (c.c_char_p, []),
         "b200bls_sm_count": (i32, []),
         "b200bls_sync": (i32, []),
+        "b200bls_set_stream": (i32, [i32]),
+        "b200bls_stream_count": (i32, []),
         "b200bls_set_ctas_per_sm": (i32, [i32]),
         "b200bls_get_ctas_per_sm": (i32, []),
         "b200bls_malloc": (vp, [sz]),

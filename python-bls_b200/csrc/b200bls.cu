@@ -64,17 +64,30 @@ struct Staging {
   size_t cap = 0;
 };
 
+constexpr int N_STREAMS = 4;
+
+// Everything a launch needs privately, so that launches on different streams can overlap:
+// the spill (cold) area, the item-block counter and the multi-stage scratch buffers.
+struct StreamCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  uint4* cold = nullptr;
+  size_t cold_bytes = 0;
+  int* counters = nullptr;   // ring of item-block counters, one per launch in flight
+  unsigned counter_pos = 0;
+  Staging scratch[6];        // device-side intermediates of multi-stage entry points
+};
+constexpr int N_COUNTERS = 256;
+
 struct Context {
   bool ready = false;
   int device = -1;
   int sm_count = 0;
-  cudaStream_t stream = nullptr;
+  StreamCtx sc[N_STREAMS];
+  int cur = 0;               // stream used by the calling API function (b200bls_set_stream)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::map<std::string, DevProgram> programs;
-  uint4* cold = nullptr;
-  size_t cold_bytes = 0;
   Staging staging[VM_MAX_BUFS];
-  Staging scratch[6];    // device-side intermediates of multi-stage entry points
   uint64_t launches = 0;
   int ctas_per_sm = 2;   // 1: 18-slot programs, 2: the "#9" variants, two CTAs per SM
 };
@@ -82,9 +95,12 @@ struct Context {
 Context g_ctx;
 std::mutex g_mu;
 
+StreamCtx& cur() { return g_ctx.sc[g_ctx.cur]; }
+#define STREAM (cur().stream)
+
 int ensure_buf(Staging& s, size_t bytes);
 int ensure_staging(int i, size_t bytes) { return ensure_buf(g_ctx.staging[i], bytes); }
-int ensure_scratch(int i, size_t bytes) { return ensure_buf(g_ctx.scratch[i], bytes); }
+int ensure_scratch(int i, size_t bytes) { return ensure_buf(cur().scratch[i], bytes); }
 
 int ensure_buf(Staging& s, size_t bytes) {
   if (s.cap >= bytes) return 0;
@@ -107,17 +123,21 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   if (grid < 1) grid = 1;
   if (grid_override > 0) grid = grid_override;
   long long total = (long long)grid * VM_NT;
+  StreamCtx& sc = cur();
   size_t cold_need = (size_t)pr.n_cold * 6 * sizeof(uint4) * total;
-  if (cold_need > c.cold_bytes) {
-    if (c.cold) cudaFree(c.cold);
-    c.cold = nullptr;
-    c.cold_bytes = 0;
+  if (cold_need > sc.cold_bytes) {
+    CU(cudaStreamSynchronize(sc.stream));
+    if (sc.cold) cudaFree(sc.cold);
+    sc.cold = nullptr;
+    sc.cold_bytes = 0;
     size_t want = (size_t)pr.n_cold * 6 * sizeof(uint4) * (size_t)max_grid * VM_NT;
     if (want < cold_need) want = cold_need;
-    cudaError_t e = cudaMalloc(&c.cold, want);
+    cudaError_t e = cudaMalloc(&sc.cold, want);
     if (e != cudaSuccess) return fail(B200BLS_E_NOMEM, "cold area cudaMalloc(%zu) failed", want);
-    c.cold_bytes = want;
+    sc.cold_bytes = want;
   }
+  int* counter = sc.counters + (sc.counter_pos++ % N_COUNTERS);
+  CU(cudaMemsetAsync(counter, 0, sizeof(int), sc.stream));
   VmParams p;
   memset(&p, 0, sizeof(p));
   p.code = pr.code;
@@ -125,12 +145,13 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   p.epi_start = pr.epi_start;
   p.n_ins = pr.n_ins;
   p.consts = pr.consts;
-  p.cold = c.cold;
+  p.cold = sc.cold;
   p.n_items = (long long)n_items;
-  p.iters = (long long)((n_items + total - 1) / total);
+  p.n_blocks = (long long)((n_items + VM_NT - 1) / VM_NT);
+  p.counter = counter;
   for (int i = 0; i < n_bufs && i < VM_MAX_BUFS; i++) p.bufs[i] = bufs[i];
   size_t smem = (size_t)pr.n_slots * 2 * 3 * sizeof(uint4) * VM_NT;
-  vm_kernel<<<grid, VM_NT, smem, c.stream>>>(p);
+  vm_kernel<<<grid, VM_NT, smem, sc.stream>>>(p);
   CU(cudaGetLastError());
   c.launches++;
   return 0;
@@ -167,13 +188,13 @@ int run_host(const char* name, size_t n, const HostBuf* hb, int n_bufs) {
     if (rc) return rc;
     bufs[i].ptr = (unsigned char*)g_ctx.staging[i].ptr;
     bufs[i].stride = (long long)hb[i].stride;
-    if (hb[i].in) CU(cudaMemcpyAsync(bufs[i].ptr, hb[i].in, hb[i].stride * n, cudaMemcpyHostToDevice, g_ctx.stream));
+    if (hb[i].in) CU(cudaMemcpyAsync(bufs[i].ptr, hb[i].in, hb[i].stride * n, cudaMemcpyHostToDevice, STREAM));
   }
   int rc = launch_program(*pr, n, bufs, n_bufs);
   if (rc) return rc;
   for (int i = 0; i < n_bufs; i++)
-    if (hb[i].out) CU(cudaMemcpyAsync(hb[i].out, bufs[i].ptr, hb[i].stride * n, cudaMemcpyDeviceToHost, g_ctx.stream));
-  CU(cudaStreamSynchronize(g_ctx.stream));
+    if (hb[i].out) CU(cudaMemcpyAsync(hb[i].out, bufs[i].ptr, hb[i].stride * n, cudaMemcpyDeviceToHost, STREAM));
+  CU(cudaStreamSynchronize(STREAM));
   return 0;
 }
 
@@ -229,7 +250,7 @@ int sum_dev(bool g2, const void* pts, void* out, size_t n) {
   const char* n2 = g2 ? "g2_sum2" : "g1_sum2";
   size_t w = g2 ? 192 : 96;
   if (n == 0) {  // empty sum = point at infinity = zero bytes
-    CU(cudaMemsetAsync(out, 0, w, g_ctx.stream));
+    CU(cudaMemsetAsync(out, 0, w, STREAM));
     return 0;
   }
   const DevProgram* p1 = find_program(n1);
@@ -238,10 +259,10 @@ int sum_dev(bool g2, const void* pts, void* out, size_t n) {
   size_t raw_bytes = (size_t)(g2 ? 3 : 2) * 6 * sizeof(uint4) * grid;
   int rc = ensure_scratch(0, raw_bytes);
   if (rc) return rc;
-  VmBuf b1[2] = {vb(pts, (long long)w), vb(g_ctx.scratch[0].ptr, grid)};
+  VmBuf b1[2] = {vb(pts, (long long)w), vb(cur().scratch[0].ptr, grid)};
   rc = launch_program(*p1, n, b1, 2, grid);
   if (rc) return rc;
-  VmBuf b2[2] = {vb(g_ctx.scratch[0].ptr, grid), vb(out, (long long)w)};
+  VmBuf b2[2] = {vb(cur().scratch[0].ptr, grid), vb(out, (long long)w)};
   return launch_named(n2, (size_t)grid, b2, 2, 1);
 }
 
@@ -252,7 +273,7 @@ int miller_product_dev(const void* P, const void* Q, void* out576, size_t n) {
   if (n == 0) return fail(B200BLS_E_ARG, "pairing_multi needs at least one pair");
   int rc = ensure_scratch(1, (size_t)576 * n);
   if (rc) return rc;
-  VmBuf ba[3] = {vb(P, 96), vb(Q, 192), vb(g_ctx.scratch[1].ptr, (long long)n)};
+  VmBuf ba[3] = {vb(P, 96), vb(Q, 192), vb(cur().scratch[1].ptr, (long long)n)};
   rc = launch_named("miller_raw", n, ba, 3);
   if (rc) return rc;
   const DevProgram* p1 = find_program("f12_prod1");
@@ -260,10 +281,10 @@ int miller_product_dev(const void* P, const void* Q, void* out576, size_t n) {
   int grid = grid_for(*p1, n);
   rc = ensure_scratch(2, (size_t)576 * grid);
   if (rc) return rc;
-  VmBuf bb[2] = {vb(g_ctx.scratch[1].ptr, (long long)n), vb(g_ctx.scratch[2].ptr, grid)};
+  VmBuf bb[2] = {vb(cur().scratch[1].ptr, (long long)n), vb(cur().scratch[2].ptr, grid)};
   rc = launch_program(*p1, n, bb, 2, grid);
   if (rc) return rc;
-  VmBuf bc[2] = {vb(g_ctx.scratch[2].ptr, grid), vb(out576, 576)};
+  VmBuf bc[2] = {vb(cur().scratch[2].ptr, grid), vb(out576, 576)};
   return launch_named("f12_prod2", (size_t)grid, bc, 2, 1);
 }
 
@@ -271,7 +292,7 @@ int sha_stage_dev(const void* hashes, void* out256, size_t n) {
   long long threads = (long long)n * 8;
   int block = 256;
   long long grid = (threads + block - 1) / block;
-  sha_stage_kernel<<<(unsigned)grid, block, 0, g_ctx.stream>>>((const uint8_t*)hashes, (uint8_t*)out256, (long long)n);
+  sha_stage_kernel<<<(unsigned)grid, block, 0, STREAM>>>((const uint8_t*)hashes, (uint8_t*)out256, (long long)n);
   CU(cudaGetLastError());
   g_ctx.launches++;
   return 0;
@@ -282,9 +303,9 @@ int hash_to_g2_dev(const void* hashes, void* out, size_t n) {
   if (n == 0) return 0;
   int rc = ensure_scratch(3, (size_t)256 * n);
   if (rc) return rc;
-  rc = sha_stage_dev(hashes, g_ctx.scratch[3].ptr, n);
+  rc = sha_stage_dev(hashes, cur().scratch[3].ptr, n);
   if (rc) return rc;
-  VmBuf b[2] = {vb(g_ctx.scratch[3].ptr, 256), vb(out, 192)};
+  VmBuf b[2] = {vb(cur().scratch[3].ptr, 256), vb(out, 192)};
   return launch_named("hash_to_g2", n, b, 2);
 }
 
@@ -293,9 +314,9 @@ int verify_dev(const void* pk, const void* mh, const void* sig, void* ok, size_t
   if (n == 0) return 0;
   int rc = ensure_scratch(4, (size_t)192 * n);
   if (rc) return rc;
-  rc = hash_to_g2_dev(mh, g_ctx.scratch[4].ptr, n);
+  rc = hash_to_g2_dev(mh, cur().scratch[4].ptr, n);
   if (rc) return rc;
-  VmBuf b[4] = {vb(pk, 96), vb(g_ctx.scratch[4].ptr, 192), vb(sig, 192), vb(ok, 1)};
+  VmBuf b[4] = {vb(pk, 96), vb(cur().scratch[4].ptr, 192), vb(sig, 192), vb(ok, 1)};
   return launch_named("verify_pair", n, b, 4);
 }
 
@@ -318,12 +339,12 @@ int compress_dev(bool g2, const void* aff, void* out, size_t n) {
   int rc = ensure_scratch(5, n);
   if (rc) return rc;
   int xb = g2 ? 96 : 48;
-  VmBuf b[2] = {vb(aff, 2 * xb), vb(g_ctx.scratch[5].ptr, 1)};
+  VmBuf b[2] = {vb(aff, 2 * xb), vb(cur().scratch[5].ptr, 1)};
   rc = launch_named(g2 ? "g2_cflag" : "g1_cflag", n, b, 2);
   if (rc) return rc;
   long long threads = (long long)n * (xb / 4);
-  compress_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, g_ctx.stream>>>(
-      (const uint8_t*)aff, (const uint8_t*)g_ctx.scratch[5].ptr, (uint8_t*)out, (long long)n, xb);
+  compress_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, STREAM>>>(
+      (const uint8_t*)aff, (const uint8_t*)cur().scratch[5].ptr, (uint8_t*)out, (long long)n, xb);
   CU(cudaGetLastError());
   g_ctx.launches++;
   return 0;
@@ -345,13 +366,13 @@ int with_staging(const HostIO* io, int n_io, F&& body) {
     int rc = ensure_staging(i, io[i].bytes ? io[i].bytes : 1);
     if (rc) return rc;
     dev[i] = g_ctx.staging[i].ptr;
-    if (io[i].in && io[i].bytes) CU(cudaMemcpyAsync(dev[i], io[i].in, io[i].bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+    if (io[i].in && io[i].bytes) CU(cudaMemcpyAsync(dev[i], io[i].in, io[i].bytes, cudaMemcpyHostToDevice, STREAM));
   }
   int rc = body(dev);
   if (rc) return rc;
   for (int i = 0; i < n_io; i++)
-    if (io[i].out && io[i].bytes) CU(cudaMemcpyAsync(io[i].out, dev[i], io[i].bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
-  CU(cudaStreamSynchronize(g_ctx.stream));
+    if (io[i].out && io[i].bytes) CU(cudaMemcpyAsync(io[i].out, dev[i], io[i].bytes, cudaMemcpyDeviceToHost, STREAM));
+  CU(cudaStreamSynchronize(STREAM));
   return 0;
 }
 
@@ -387,7 +408,12 @@ int b200bls_init(int device) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c.sm_count = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  for (auto& sc : c.sc) {
+    CU(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming));
+    CU(cudaMalloc(&sc.counters, N_COUNTERS * sizeof(int)));
+  }
+  c.cur = 0;
   CU(cudaEventCreate(&c.ev0));
   CU(cudaEventCreate(&c.ev1));
   CU(cudaFuncSetAttribute(vm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -428,7 +454,7 @@ void b200bls_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   Context& c = g_ctx;
   if (!c.ready) return;
-  cudaStreamSynchronize(c.stream);
+  for (auto& sc : c.sc) cudaStreamSynchronize(sc.stream);
   for (auto& kv : c.programs) {
     cudaFree(kv.second.code);
     cudaFree(kv.second.consts);
@@ -439,17 +465,21 @@ void b200bls_shutdown(void) {
     s.ptr = nullptr;
     s.cap = 0;
   }
-  for (auto& s : c.scratch) {
-    if (s.ptr) cudaFree(s.ptr);
-    s.ptr = nullptr;
-    s.cap = 0;
+  for (auto& sc : c.sc) {
+    for (auto& s : sc.scratch) {
+      if (s.ptr) cudaFree(s.ptr);
+      s.ptr = nullptr;
+      s.cap = 0;
+    }
+    if (sc.cold) cudaFree(sc.cold);
+    sc.cold = nullptr;
+    sc.cold_bytes = 0;
+    cudaFree(sc.counters);
+    cudaEventDestroy(sc.done);
+    cudaStreamDestroy(sc.stream);
   }
-  if (c.cold) cudaFree(c.cold);
-  c.cold = nullptr;
-  c.cold_bytes = 0;
   cudaEventDestroy(c.ev0);
   cudaEventDestroy(c.ev1);
-  cudaStreamDestroy(c.stream);
   c.ready = false;
   c.device = -1;
 }
@@ -467,9 +497,18 @@ int b200bls_get_ctas_per_sm(void) { return g_ctx.ctas_per_sm; }
 
 int b200bls_sync(void) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
-  CU(cudaStreamSynchronize(g_ctx.stream));
+  for (auto& sc : g_ctx.sc) CU(cudaStreamSynchronize(sc.stream));
   return 0;
 }
+
+int b200bls_set_stream(int idx) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (idx < 0 || idx >= N_STREAMS) return fail(B200BLS_E_ARG, "stream index out of range (0..%d)", N_STREAMS - 1);
+  g_ctx.cur = idx;
+  return 0;
+}
+
+int b200bls_stream_count(void) { return N_STREAMS; }
 
 void* b200bls_malloc(size_t bytes) {
   if (!g_ctx.ready) {
@@ -509,25 +548,32 @@ void b200bls_host_free(void* p) {
 
 int b200bls_h2d(void* dst, const void* src, size_t bytes) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
-  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, STREAM));
   return 0;
 }
 
 int b200bls_d2h(void* dst, const void* src, size_t bytes) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
-  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, STREAM));
   return 0;
 }
 
+// The timed region covers ALL library streams: every stream waits for the start event, and
+// the stop event is recorded on stream 0 after it has waited for the work of every other one.
 int b200bls_timer_start(void) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
-  CU(cudaEventRecord(g_ctx.ev0, g_ctx.stream));
+  CU(cudaEventRecord(g_ctx.ev0, g_ctx.sc[0].stream));
+  for (int i = 1; i < N_STREAMS; i++) CU(cudaStreamWaitEvent(g_ctx.sc[i].stream, g_ctx.ev0, 0));
   return 0;
 }
 
 int b200bls_timer_stop(float* ms) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
-  CU(cudaEventRecord(g_ctx.ev1, g_ctx.stream));
+  for (int i = 1; i < N_STREAMS; i++) {
+    CU(cudaEventRecord(g_ctx.sc[i].done, g_ctx.sc[i].stream));
+    CU(cudaStreamWaitEvent(g_ctx.sc[0].stream, g_ctx.sc[i].done, 0));
+  }
+  CU(cudaEventRecord(g_ctx.ev1, g_ctx.sc[0].stream));
   CU(cudaEventSynchronize(g_ctx.ev1));
   CU(cudaEventElapsedTime(ms, g_ctx.ev0, g_ctx.ev1));
   return 0;
@@ -735,9 +781,9 @@ int b200bls_pairing_multi_dev(const void* P, const void* Q, void* out, size_t n)
   NEED_READY();
   int rc = ensure_scratch(5, 576);
   if (rc) return rc;
-  rc = miller_product_dev(P, Q, g_ctx.scratch[5].ptr, n);
+  rc = miller_product_dev(P, Q, cur().scratch[5].ptr, n);
   if (rc) return rc;
-  VmBuf b[2] = {vb(g_ctx.scratch[5].ptr, 576), vb(out, 576)};
+  VmBuf b[2] = {vb(cur().scratch[5].ptr, 576), vb(out, 576)};
   return launch_named("final_exp", 1, b, 2);
 }
 int b200bls_verify_batch(const uint8_t* pk, const uint8_t* mh, const uint8_t* sig, uint8_t* ok, size_t n) {
@@ -774,19 +820,19 @@ int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8
   uint8_t* dM = (uint8_t*)g_ctx.staging[1].ptr;
   uint8_t* dQ = (uint8_t*)g_ctx.staging[2].ptr;
   uint8_t* dF = (uint8_t*)g_ctx.staging[3].ptr;
-  CU(cudaMemcpyAsync(dP, kNegG1, 96, cudaMemcpyHostToDevice, g_ctx.stream));
-  CU(cudaMemcpyAsync(dQ, sig, 192, cudaMemcpyHostToDevice, g_ctx.stream));
+  CU(cudaMemcpyAsync(dP, kNegG1, 96, cudaMemcpyHostToDevice, STREAM));
+  CU(cudaMemcpyAsync(dQ, sig, 192, cudaMemcpyHostToDevice, STREAM));
   if (n) {
-    CU(cudaMemcpyAsync(dP + 96, pks, 96 * n, cudaMemcpyHostToDevice, g_ctx.stream));
-    CU(cudaMemcpyAsync(dM, mhs, 32 * n, cudaMemcpyHostToDevice, g_ctx.stream));
+    CU(cudaMemcpyAsync(dP + 96, pks, 96 * n, cudaMemcpyHostToDevice, STREAM));
+    CU(cudaMemcpyAsync(dM, mhs, 32 * n, cudaMemcpyHostToDevice, STREAM));
     if ((rc = hash_to_g2_dev(dM, dQ + 192, n))) return rc;
   }
   if ((rc = miller_product_dev(dP, dQ, dF, n + 1))) return rc;
   VmBuf b[2] = {vb(dF, 576), vb(dF + 576, 576)};
   if ((rc = launch_named("final_exp", 1, b, 2))) return rc;
   uint8_t res[576];
-  CU(cudaMemcpyAsync(res, dF + 576, 576, cudaMemcpyDeviceToHost, g_ctx.stream));
-  CU(cudaStreamSynchronize(g_ctx.stream));
+  CU(cudaMemcpyAsync(res, dF + 576, 576, cudaMemcpyDeviceToHost, STREAM));
+  CU(cudaStreamSynchronize(STREAM));
   bool one = res[47] == 1;
   for (int i = 0; i < 576 && one; i++)
     if (i != 47 && res[i] != 0) one = false;

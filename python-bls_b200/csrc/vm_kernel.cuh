@@ -29,7 +29,8 @@ struct VmParams {
   const uint4* consts;     // Montgomery-form constants, 3 x uint4 each
   uint4* cold;             // [n_cold * 6][total threads]
   long long n_items;
-  long long iters;         // body repetitions = ceil(n_items / total threads)
+  long long n_blocks;      // ceil(n_items / VM_NT): item blocks handed out dynamically
+  int* counter;            // zeroed before the launch; next item block to process
   VmBuf bufs[VM_MAX_BUFS];
 };
 
@@ -198,20 +199,34 @@ __global__ void __launch_bounds__(VM_NT, 2) vm_kernel(const __grid_constant__ Vm
   const long long last = p.n_items > 0 ? p.n_items - 1 : 0;
   env.item_raw = gtid;
   env.item = gtid < last ? gtid : last;
-  // prologue once, body `iters` times, epilogue once -- one copy of the interpreter loop
-  for (long long rep = 0; rep < p.iters + 2; rep++) {
+  // prologue once; then item blocks of VM_NT items are fetched from a global counter until the
+  // batch is exhausted (CTAs that find no work left exit early, so the CTAs of the next launch
+  // on another stream can move in: no tail-wave quantisation across back-to-back batches);
+  // epilogue once.  One copy of the interpreter loop serves all three sections.
+  __shared__ int s_blk;
+  for (int phase = 0; phase < 3;) {
     int lo, hi;
-    if (rep == 0) {
+    if (phase == 0) {
       lo = 0;
       hi = p.body_start;
-    } else if (rep <= p.iters) {
+      phase = 1;
+    } else if (phase == 1) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_blk = atomicAdd(p.counter, 1);
+      __syncthreads();
+      const long long blk = s_blk;
+      if (blk >= p.n_blocks) {
+        phase = 2;
+        continue;
+      }
       lo = p.body_start;
       hi = p.epi_start;
-      env.item_raw = (rep - 1) * env.total + gtid;
+      env.item_raw = blk * VM_NT + threadIdx.x;
       env.item = env.item_raw < last ? env.item_raw : last;
     } else {
       lo = p.epi_start;
       hi = p.n_ins;
+      phase = 3;
     }
     vm_run_section(env, p.code, lo, hi);
   }
