@@ -1,11 +1,13 @@
 """Name -> builder table of every VM program embedded into libb200bls.so."""
 from . import curve, fieldops, hashg2, pairing
 
-# Fq2 slots per thread.  One CTA of 128 threads per SM gets 18 slots (216 KB of shared memory);
-# two co-resident CTAs per SM get 9 slots each and hide each other's latencies.  Every program
-# is assembled for both shapes; the variant for n != 18 is named "<name>#<n>".
+# Launch shapes: CTAs (of 128 threads) per SM -> (Fq2 slots per thread in shared memory, slots in
+# Tensor Memory).  Shared memory: ctas * slots * 96 B * 128 <= 227 KB; TMEM: ctas * pow2(24 *
+# slots) <= 512 columns.  Every program is assembled for every shape ("<name>@<ctas>"); when a
+# program cannot use TMEM (cross-thread reads) the shared-memory-only shape is used, and when
+# it does not fit a shape at all the launcher falls back to fewer CTAs per SM.
 N_SLOTS = 18
-SLOT_VARIANTS = (18, 9)
+SHAPES = {1: (18, 21), 2: (9, 10), 3: (6, 5)}
 
 PROGRAMS = {}
 for _level in (1, 2, 6, 12):

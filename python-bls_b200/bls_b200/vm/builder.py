@@ -370,8 +370,15 @@ class Program:
         return r
 
     # ---- assembly ---------------------------------------------------------------------------
-    def assemble(self, n_slots, n_cold=1024):
-        return _assemble(self, n_slots, n_cold)
+    def assemble(self, n_slots, n_cold=1024, n_tmem=0):
+        """n_slots Fq2 slots in shared memory plus n_tmem slots in Tensor Memory (slot indices
+        n_slots .. n_slots + n_tmem - 1).  TMEM lanes are private to their thread, so programs
+        with cross-thread reads (XMOV2) must be assembled with n_tmem = 0."""
+        if n_tmem and any(op.name == "XMOV2" for op in self.ops):
+            raise RuntimeError("cross-thread reads need a shared-memory-only workspace")
+        asm = _assemble(self, n_slots + n_tmem, n_cold)
+        asm.n_slots, asm.n_tmem = n_slots, n_tmem
+        return asm
 
 
 class Assembled:
@@ -382,7 +389,8 @@ class Assembled:
         self.code = code
         self.consts = consts
         self.body_start, self.epilogue_start = marks
-        self.n_slots = n_slots
+        self.n_slots = n_slots      # shared-memory slots
+        self.n_tmem = 0             # Tensor Memory slots (indices after the shared ones)
         self.n_cold = n_cold
         self.stats = stats
 

@@ -66,10 +66,31 @@ N_FLAGS = 32
 INS_BYTES = 8
 
 
+# operand handling done once by the interpreter, outside the per-opcode switch
+INFO_A1, INFO_A2, INFO_B1, INFO_B2, INFO_D1, INFO_D2 = 1, 2, 4, 8, 16, 32
+_CUSTOM_OPERANDS = {"XMOV2": INFO_D2, "SPILL2": INFO_A2, "FILL2": INFO_D2, "CSEL2": INFO_A2 | INFO_B2 | INFO_D2,
+                    "CSEL1": INFO_A1 | INFO_B1 | INFO_D1}
+
+
+def op_info(name):
+    if name in _CUSTOM_OPERANDS:
+        return _CUSTOM_OPERANDS[name]
+    sig = OPSIG[name] + ["-"] * 3
+    bits = 0
+    bits |= {"c1": INFO_D1, "c2": INFO_D2}.get(sig[0], 0)
+    bits |= {"c1": INFO_A1, "c2": INFO_A2}.get(sig[1], 0)
+    bits |= {"c1": INFO_B1, "c2": INFO_B2}.get(sig[2], 0)
+    return bits
+
+
 def c_header():
     lines = ["// generated from bls_b200/vm/isa.py -- do not edit", "#pragma once", "enum VmOp : int {"]
     for i, (name, sig, doc) in enumerate(OPS):
         lines.append("  OP_%s = %d,%s" % (name, i, ("  // " + (sig + "  " + doc).strip()) if (sig or doc) else ""))
     lines.append("  OP__COUNT = %d" % len(OPS))
     lines.append("};")
+    lines.append("// operand handling per opcode: bit0/1 load a as Fq/Fq2, bit2/3 load b as Fq/Fq2,")
+    lines.append("// bit4/5 store the result to d as Fq/Fq2")
+    lines.append("enum VmOpInfo : unsigned { VM_A1 = 1, VM_A2 = 2, VM_B1 = 4, VM_B2 = 8, VM_D1 = 16, VM_D2 = 32 };")
+    lines.append("#define VM_OP_INFO_TABLE {%s}" % ", ".join(str(op_info(n)) for n, _, _ in OPS))
     return "\n".join(lines) + "\n"

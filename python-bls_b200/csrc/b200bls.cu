@@ -48,15 +48,15 @@ int fail(int code, const char* fmt, ...) {
 
 struct BlobEntry {
   char name[32];
-  uint32_t n_ins, body_start, epi_start, n_consts, n_slots, n_cold;
+  uint32_t n_ins, body_start, epi_start, n_consts, n_slots, n_cold, n_tmem, ctas;
   uint64_t code_off, consts_off;
 };
-static_assert(sizeof(BlobEntry) == 32 + 24 + 16, "blob entry layout");
+static_assert(sizeof(BlobEntry) == 32 + 32 + 16, "blob entry layout");
 
 struct DevProgram {
   uint2* code = nullptr;
   uint4* consts = nullptr;
-  int n_ins = 0, body_start = 0, epi_start = 0, n_slots = 0, n_cold = 0;
+  int n_ins = 0, body_start = 0, epi_start = 0, n_slots = 0, n_cold = 0, n_tmem = 0, ctas = 1;
 };
 
 struct Staging {
@@ -118,7 +118,7 @@ int ensure_buf(Staging& s, size_t bytes) {
 int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int n_bufs, int grid_override = 0) {
   Context& c = g_ctx;
   long long blocks_needed = (long long)((n_items + VM_NT - 1) / VM_NT);
-  long long max_grid = (long long)c.sm_count * (pr.n_slots <= 9 ? 2 : 1);
+  long long max_grid = (long long)c.sm_count * pr.ctas;
   int grid = (int)(blocks_needed < max_grid ? blocks_needed : max_grid);
   if (grid < 1) grid = 1;
   if (grid_override > 0) grid = grid_override;
@@ -149,6 +149,8 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   p.n_items = (long long)n_items;
   p.n_blocks = (long long)((n_items + VM_NT - 1) / VM_NT);
   p.counter = counter;
+  p.smem_cells = 2 * pr.n_slots;
+  p.tmem_cols = pr.n_tmem == 0 ? 0 : (pr.n_tmem * 24 <= 128 ? 128 : (pr.n_tmem * 24 <= 256 ? 256 : 512));
   for (int i = 0; i < n_bufs && i < VM_MAX_BUFS; i++) p.bufs[i] = bufs[i];
   size_t smem = (size_t)pr.n_slots * 2 * 3 * sizeof(uint4) * VM_NT;
   vm_kernel<<<grid, VM_NT, smem, sc.stream>>>(p);
@@ -158,15 +160,19 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
 }
 
 const DevProgram* find_program(const char* base) {
+  // "<name>@<ctas>": the configured shape, else the nearest one with fewer CTAs per SM
   std::string name(base);
-  if (g_ctx.ctas_per_sm == 2 && name.find('#') == std::string::npos) name += "#9";
-  auto it = g_ctx.programs.find(name);
-  if (it == g_ctx.programs.end()) it = g_ctx.programs.find(base);  // no 9-slot variant: 1 CTA/SM
-  if (it == g_ctx.programs.end()) {
-    fail(B200BLS_E_PROGRAM, "unknown program '%s'", name.c_str());
-    return nullptr;
+  if (name.find('@') != std::string::npos) {
+    auto it = g_ctx.programs.find(name);
+    if (it != g_ctx.programs.end()) return &it->second;
+  } else {
+    for (int c = g_ctx.ctas_per_sm; c >= 1; c--) {
+      auto it = g_ctx.programs.find(name + "@" + std::to_string(c));
+      if (it != g_ctx.programs.end()) return &it->second;
+    }
   }
-  return &it->second;
+  fail(B200BLS_E_PROGRAM, "unknown program '%s'", base);
+  return nullptr;
 }
 
 struct HostBuf {
@@ -175,27 +181,44 @@ struct HostBuf {
   size_t stride;    // bytes per item
 };
 
-// copy inputs up, run, copy outputs back, synchronise
+// copy inputs up, run, copy outputs back, synchronise.  Large batches are cut into chunks
+// that go to alternating streams: the H2D copy of one chunk overlaps the kernel of another,
+// and the dynamically scheduled CTAs of consecutive chunks fill each other's tail waves.
 int run_host(const char* name, size_t n, const HostBuf* hb, int n_bufs) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "b200bls_init() has not succeeded");
   const DevProgram* pr = find_program(name);
   if (!pr) return B200BLS_E_PROGRAM;
   if (n == 0) return 0;
-  VmBuf bufs[VM_MAX_BUFS];
-  memset(bufs, 0, sizeof(bufs));
   for (int i = 0; i < n_bufs; i++) {
     int rc = ensure_staging(i, hb[i].stride * n);
     if (rc) return rc;
-    bufs[i].ptr = (unsigned char*)g_ctx.staging[i].ptr;
-    bufs[i].stride = (long long)hb[i].stride;
-    if (hb[i].in) CU(cudaMemcpyAsync(bufs[i].ptr, hb[i].in, hb[i].stride * n, cudaMemcpyHostToDevice, STREAM));
   }
-  int rc = launch_program(*pr, n, bufs, n_bufs);
-  if (rc) return rc;
-  for (int i = 0; i < n_bufs; i++)
-    if (hb[i].out) CU(cudaMemcpyAsync(hb[i].out, bufs[i].ptr, hb[i].stride * n, cudaMemcpyDeviceToHost, STREAM));
-  CU(cudaStreamSynchronize(STREAM));
-  return 0;
+  const size_t wave = (size_t)g_ctx.sm_count * pr->ctas * VM_NT;
+  size_t n_chunks = n >= 2 * wave ? 4 : 1;
+  size_t per = ((n + n_chunks - 1) / n_chunks + VM_NT - 1) / VM_NT * VM_NT;
+  const int home = g_ctx.cur;
+  int rc = 0;
+  for (size_t c = 0, lo = 0; lo < n && !rc; c++, lo += per) {
+    size_t cnt = n - lo < per ? n - lo : per;
+    g_ctx.cur = (home + (int)(c % 2)) % N_STREAMS;
+    VmBuf bufs[VM_MAX_BUFS];
+    memset(bufs, 0, sizeof(bufs));
+    for (int i = 0; i < n_bufs; i++) {
+      bufs[i].ptr = (unsigned char*)g_ctx.staging[i].ptr + lo * hb[i].stride;
+      bufs[i].stride = (long long)hb[i].stride;
+      if (hb[i].in)
+        CU(cudaMemcpyAsync(bufs[i].ptr, (const unsigned char*)hb[i].in + lo * hb[i].stride, hb[i].stride * cnt,
+                           cudaMemcpyHostToDevice, STREAM));
+    }
+    rc = launch_program(*pr, cnt, bufs, n_bufs);
+    for (int i = 0; i < n_bufs && !rc; i++)
+      if (hb[i].out)
+        CU(cudaMemcpyAsync((unsigned char*)hb[i].out + lo * hb[i].stride, bufs[i].ptr, hb[i].stride * cnt,
+                           cudaMemcpyDeviceToHost, STREAM));
+  }
+  g_ctx.cur = home;
+  for (int k = 0; k < 2; k++) CU(cudaStreamSynchronize(g_ctx.sc[(home + k) % N_STREAMS].stream));
+  return rc;
 }
 
 struct DevBuf {
@@ -220,7 +243,7 @@ int run_dev(const char* name, size_t n, const DevBuf* db, int n_bufs) {
 
 int grid_for(const DevProgram& pr, size_t n_items) {
   long long blocks_needed = (long long)((n_items + VM_NT - 1) / VM_NT);
-  long long max_grid = (long long)g_ctx.sm_count * (pr.n_slots <= 9 ? 2 : 1);
+  long long max_grid = (long long)g_ctx.sm_count * pr.ctas;
   long long g = blocks_needed < max_grid ? blocks_needed : max_grid;
   return g < 1 ? 1 : (int)g;
 }
@@ -416,11 +439,14 @@ int b200bls_init(int device) {
   c.cur = 0;
   CU(cudaEventCreate(&c.ev0));
   CU(cudaEventCreate(&c.ev1));
-  CU(cudaFuncSetAttribute(vm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(vm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   // parse the embedded program blob
   const unsigned char* blob = _binary_programs_bin_start;
   size_t blob_len = (size_t)(_binary_programs_bin_end - _binary_programs_bin_start);
-  if (blob_len < 16 || memcmp(blob, "B2BLSPRG", 8) != 0) return fail(B200BLS_E_PROGRAM, "bad program blob");
+  uint32_t blob_version = 0;
+  if (blob_len >= 16) memcpy(&blob_version, blob + 8, 4);
+  if (blob_len < 16 || memcmp(blob, "B2BLSPRG", 8) != 0 || blob_version != 2)
+    return fail(B200BLS_E_PROGRAM, "bad program blob");
   uint32_t n_prog;
   memcpy(&n_prog, blob + 12, 4);
   for (uint32_t i = 0; i < n_prog; i++) {
@@ -432,6 +458,8 @@ int b200bls_init(int device) {
     dp.epi_start = (int)en.epi_start;
     dp.n_slots = (int)en.n_slots;
     dp.n_cold = (int)en.n_cold;
+    dp.n_tmem = (int)en.n_tmem;
+    dp.ctas = (int)en.ctas;
     size_t code_bytes = (size_t)(en.n_ins + 1) * sizeof(uint2);
     size_t const_bytes = (size_t)en.n_consts * 3 * sizeof(uint4);
     CU(cudaMalloc(&dp.code, code_bytes));
@@ -444,7 +472,7 @@ int b200bls_init(int device) {
     c.programs[nm] = dp;
   }
   const char* env = getenv("B200BLS_CTAS_PER_SM");
-  if (env && (env[0] == '1' || env[0] == '2')) c.ctas_per_sm = env[0] - '0';
+  if (env && env[0] >= '1' && env[0] <= '3') c.ctas_per_sm = env[0] - '0';
   c.device = device;
   c.ready = true;
   return 0;
@@ -488,7 +516,7 @@ int b200bls_sm_count(void) { return g_ctx.ready ? g_ctx.sm_count : 0; }
 
 int b200bls_set_ctas_per_sm(int n) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (n != 1 && n != 2) return fail(B200BLS_E_ARG, "ctas_per_sm must be 1 or 2");
+  if (n < 1 || n > 3) return fail(B200BLS_E_ARG, "ctas_per_sm must be 1, 2 or 3");
   g_ctx.ctas_per_sm = n;
   return 0;
 }

@@ -31,11 +31,41 @@ struct VmParams {
   long long n_items;
   long long n_blocks;      // ceil(n_items / VM_NT): item blocks handed out dynamically
   int* counter;            // zeroed before the launch; next item block to process
+  int smem_cells;          // cells [0, smem_cells) live in shared memory, the rest in Tensor Memory
+  int tmem_cols;           // TMEM columns to allocate per CTA (0, 128, 256 or 512)
   VmBuf bufs[VM_MAX_BUFS];
 };
 
+// ---- Tensor Memory as per-thread scratch --------------------------------------------------------
+// TMEM is 512 columns x 128 lanes x 32 bit per SM.  With the 32x32b access shape, thread i of
+// warp w reads/writes lane 32*(w%4)+i: a 128-thread CTA therefore owns one private lane per
+// thread, `tmem_cols` words deep -- a second on-chip workspace next to shared memory (no tensor
+// core is involved; tcgen05.ld/st only).  An fp cell is 12 columns, an Fq2 slot 24.
+__device__ __forceinline__ void tm_ld8(uint32_t addr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(addr));
+}
+__device__ __forceinline__ void tm_ld4(uint32_t addr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void tm_st8(uint32_t addr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
+}
+__device__ __forceinline__ void tm_st4(uint32_t addr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]));
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 struct DevEnv {
   uint4* sm;               // shared workspace, already offset by threadIdx.x
+  uint32_t tm_base;        // TMEM address of column 0 in this warp's lane quadrant
+  int smem_cells;
   const VmParams* p;
   uint4* cold;             // cold area, already offset by the global thread id
   long long total;
@@ -51,29 +81,63 @@ struct DevEnv {
   __device__ __forceinline__ static uint4 pack(const fp& x, int k) {
     return make_uint4(x.v[4 * k], x.v[4 * k + 1], x.v[4 * k + 2], x.v[4 * k + 3]);
   }
+  // the cell index comes from the instruction word: the shared/tensor-memory branch is
+  // warp-uniform, as tcgen05.ld/st (.sync.aligned) require
   __device__ __forceinline__ void ld1(int c, fp& x) {
-    const uint4* q = sm + c * (3 * VM_NT);
+    if (c < smem_cells) {
+      const uint4* q = sm + c * (3 * VM_NT);
 #pragma unroll
-    for (int k = 0; k < 3; k++) unpack(x, k, q[k * VM_NT]);
+      for (int k = 0; k < 3; k++) unpack(x, k, q[k * VM_NT]);
+    } else {
+      const uint32_t t = tm_base + (uint32_t)(c - smem_cells) * 12;
+      tm_wait_st();
+      tm_ld8(t, x.v);
+      tm_ld4(t + 8, x.v + 8);
+      tm_wait_ld();
+    }
   }
   __device__ __forceinline__ void st1(int c, const fp& x) {
-    uint4* q = sm + c * (3 * VM_NT);
+    if (c < smem_cells) {
+      uint4* q = sm + c * (3 * VM_NT);
 #pragma unroll
-    for (int k = 0; k < 3; k++) q[k * VM_NT] = pack(x, k);
+      for (int k = 0; k < 3; k++) q[k * VM_NT] = pack(x, k);
+    } else {
+      const uint32_t t = tm_base + (uint32_t)(c - smem_cells) * 12;
+      tm_st8(t, x.v);
+      tm_st4(t + 8, x.v + 8);
+    }
   }
   __device__ __forceinline__ void ld2(int c, fp2& x) {
-    const uint4* q = sm + c * (3 * VM_NT);
+    if (c < smem_cells) {
+      const uint4* q = sm + c * (3 * VM_NT);
 #pragma unroll
-    for (int k = 0; k < 3; k++) unpack(x.c0, k, q[k * VM_NT]);
+      for (int k = 0; k < 3; k++) unpack(x.c0, k, q[k * VM_NT]);
 #pragma unroll
-    for (int k = 0; k < 3; k++) unpack(x.c1, k, q[(3 + k) * VM_NT]);
+      for (int k = 0; k < 3; k++) unpack(x.c1, k, q[(3 + k) * VM_NT]);
+    } else {
+      const uint32_t t = tm_base + (uint32_t)(c - smem_cells) * 12;
+      tm_wait_st();
+      tm_ld8(t, x.c0.v);
+      tm_ld4(t + 8, x.c0.v + 8);
+      tm_ld8(t + 12, x.c1.v);
+      tm_ld4(t + 20, x.c1.v + 8);
+      tm_wait_ld();
+    }
   }
   __device__ __forceinline__ void st2(int c, const fp2& x) {
-    uint4* q = sm + c * (3 * VM_NT);
+    if (c < smem_cells) {
+      uint4* q = sm + c * (3 * VM_NT);
 #pragma unroll
-    for (int k = 0; k < 3; k++) q[k * VM_NT] = pack(x.c0, k);
+      for (int k = 0; k < 3; k++) q[k * VM_NT] = pack(x.c0, k);
 #pragma unroll
-    for (int k = 0; k < 3; k++) q[(3 + k) * VM_NT] = pack(x.c1, k);
+      for (int k = 0; k < 3; k++) q[(3 + k) * VM_NT] = pack(x.c1, k);
+    } else {
+      const uint32_t t = tm_base + (uint32_t)(c - smem_cells) * 12;
+      tm_st8(t, x.c0.v);
+      tm_st4(t + 8, x.c0.v + 8);
+      tm_st8(t + 12, x.c1.v);
+      tm_st4(t + 20, x.c1.v + 8);
+    }
   }
   __device__ __forceinline__ void ld2_lane(int c, int off, fp2& x) {
     int t = (threadIdx.x + off) % VM_NT;
@@ -187,9 +251,30 @@ __device__ __forceinline__ void vm_run_section(DevEnv& env, const uint2* code, i
   }
 }
 
-__global__ void __launch_bounds__(VM_NT, 2) vm_kernel(const __grid_constant__ VmParams p) {
+__global__ void __launch_bounds__(VM_NT, 3) vm_kernel(const __grid_constant__ VmParams p) {
   extern __shared__ uint4 vm_smem[];
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_blk;
   DevEnv env;
+  env.smem_cells = p.smem_cells;
+  env.tm_base = 0;
+  if (p.tmem_cols) {
+    // warp 0 allocates this CTA's columns; co-resident CTAs share the SM's 512
+    if (threadIdx.x < 32) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_tmem);
+      if (p.tmem_cols == 128)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(dst));
+      else if (p.tmem_cols == 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(dst));
+      else
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(dst));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    env.tm_base = s_tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+  }
   env.sm = vm_smem + threadIdx.x;
   env.p = &p;
   env.total = (long long)gridDim.x * VM_NT;
@@ -203,7 +288,6 @@ __global__ void __launch_bounds__(VM_NT, 2) vm_kernel(const __grid_constant__ Vm
   // batch is exhausted (CTAs that find no work left exit early, so the CTAs of the next launch
   // on another stream can move in: no tail-wave quantisation across back-to-back batches);
   // epilogue once.  One copy of the interpreter loop serves all three sections.
-  __shared__ int s_blk;
   for (int phase = 0; phase < 3;) {
     int lo, hi;
     if (phase == 0) {
@@ -229,6 +313,19 @@ __global__ void __launch_bounds__(VM_NT, 2) vm_kernel(const __grid_constant__ Vm
       phase = 3;
     }
     vm_run_section(env, p.code, lo, hi);
+  }
+  if (p.tmem_cols) {
+    tm_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      if (p.tmem_cols == 128)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(s_tmem));
+      else if (p.tmem_cols == 256)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(s_tmem));
+      else
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(s_tmem));
+    }
   }
 }
 

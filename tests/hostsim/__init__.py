@@ -36,7 +36,7 @@ def run(asm, bufs, strides, n_items, n_blocks=1, nt=4, honor_skips=True):
             st[i] = strides.get(i, 0)
     rc = lib().hs_vm_run(code.ctypes.data_as(ctypes.c_void_p), len(asm.code), asm.body_start,
                          asm.epilogue_start, consts.ctypes.data_as(ctypes.c_void_p),
-                         asm.n_slots, max(asm.stats["max_cold"], 1), ptrs, st,
+                         asm.n_slots, asm.n_tmem, max(asm.stats["max_cold"], 1), ptrs, st,
                          ctypes.c_long(n_items), n_blocks, nt, int(honor_skips))
     assert rc == 0
     return bufs

@@ -19,6 +19,7 @@ struct Shared {
   long n_items;
   int nt, n_blocks, total;
   int n_cells;
+  int smem_cells;                // cells >= smem_cells model Tensor Memory (thread-private)
   std::vector<uint32_t>* smem;   // per block: [cell][chunk][tid][4]
   std::vector<uint32_t> cold;    // [(g*6+k)*total + gtid][4]
 };
@@ -41,6 +42,7 @@ struct HostEnv {
   void ld2(int c, fp2& x) { ld1(c, x.c0); ld1(c + 1, x.c1); }
   void st2(int c, const fp2& x) { st1(c, x.c0); st1(c + 1, x.c1); }
   void ld2_lane(int c, int off, fp2& x) {
+    if (c + 1 >= sh->smem_cells) abort();  // TMEM lanes cannot be read by another thread
     int t = (tid + off) % sh->nt;
     for (int k = 0; k < 3; k++) {
       memcpy(&x.c0.v[4 * k], cellp(c, k, t), 16);
@@ -124,7 +126,7 @@ struct HostEnv {
 }  // namespace
 
 extern "C" int hs_vm_run(const uint32_t* code, int n_ins, int body_start, int epi_start,
-                         const uint32_t* consts, int n_slots, int n_cold, uint8_t** bufs,
+                         const uint32_t* consts, int n_slots, int n_tmem, int n_cold, uint8_t** bufs,
                          const long* strides, long n_items, int n_blocks, int nt,
                          int honor_skips) {
   Shared sh;
@@ -134,7 +136,8 @@ extern "C" int hs_vm_run(const uint32_t* code, int n_ins, int body_start, int ep
   sh.nt = nt;
   sh.n_blocks = n_blocks;
   sh.total = nt * n_blocks;
-  sh.n_cells = 2 * n_slots;
+  sh.n_cells = 2 * (n_slots + n_tmem);
+  sh.smem_cells = 2 * n_slots;
   std::vector<std::vector<uint32_t>> smem(n_blocks);
   for (auto& s : smem) s.assign((size_t)sh.n_cells * 3 * nt * 4, 0xdeadbeefu);
   sh.smem = smem.data();

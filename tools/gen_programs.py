@@ -3,8 +3,8 @@
 
 Blob layout (little endian):
   char magic[8] = "B2BLSPRG"; u32 version; u32 n_programs;
-  n_programs x { char name[32]; u32 n_ins, body_start, epi_start, n_consts, n_slots, n_cold;
-                 u64 code_off, consts_off; }
+  n_programs x { char name[32]; u32 n_ins, body_start, epi_start, n_consts, n_slots (shared),
+                 n_cold, n_tmem (Tensor Memory slots), ctas_per_sm; u64 code_off, consts_off; }
   code:   (n_ins + 1) x 8 bytes (one trailing NOP of padding)
   consts: n_consts x 12 x u32 Montgomery-form limbs
 """
@@ -25,26 +25,31 @@ def main(out_path=None):
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     progs = []
     for base, builder in registry.PROGRAMS.items():
-        for n_slots in registry.SLOT_VARIANTS:
-            name = base if n_slots == registry.N_SLOTS else "%s#%d" % (base, n_slots)
+        for ctas, (n_slots, n_tmem) in registry.SHAPES.items():
+            name = "%s@%d" % (base, ctas)
             t = time.time()
-            try:
-                asm = builder().assemble(n_slots, n_cold=4096)
-            except RuntimeError as e:
-                if n_slots == registry.N_SLOTS:
-                    raise
-                # the launcher falls back to the 18-slot (one CTA per SM) variant
-                print("%-24s not available: %s" % (name, e))
+            asm = None
+            for tm in ((n_tmem, 0) if n_tmem else (0,)):
+                try:
+                    asm = builder().assemble(n_slots, n_cold=4096, n_tmem=tm)
+                    break
+                except RuntimeError as e:
+                    err = e
+            if asm is None:
+                if ctas == 1:
+                    raise err
+                print("%-24s not available: %s" % (name, err))
                 continue
-            print("%-24s %6d ins  spills %5d fills %5d cold %3d  (%.1fs)" % (
-                name, asm.stats["n_ins"], asm.stats["spills"], asm.stats["fills"],
+            print("%-24s %6d ins  slots %2d+%2d  spills %5d fills %5d cold %3d  (%.1fs)" % (
+                name, asm.stats["n_ins"], asm.n_slots, asm.n_tmem, asm.stats["spills"], asm.stats["fills"],
                 asm.stats["max_cold"], time.time() - t))
-            progs.append((name, asm))
-    head = 16 + len(progs) * (32 + 6 * 4 + 2 * 8)
+            progs.append((name, ctas, asm))
+    entry = "<32s8I2Q"
+    head = 16 + len(progs) * struct.calcsize(entry)
     blobs = []
     off = head
     table = b""
-    for name, asm in progs:
+    for name, ctas, asm in progs:
         code = np.concatenate([asm.code, np.zeros((1, 4), dtype=np.uint16)]).astype("<u2").tobytes()
         consts = asm.const_limbs().astype("<u4").tobytes()
         n_consts = max(1, len(asm.consts))
@@ -54,12 +59,11 @@ def main(out_path=None):
         off = (off + 15) & ~15
         consts_off = off
         off += len(consts)
-        table += struct.pack("<32s6I2Q", name.encode(), len(asm.code), asm.body_start,
-                             asm.epilogue_start, n_consts, asm.n_slots,
-                             max(1, asm.stats["max_cold"]), code_off, consts_off)
+        table += struct.pack(entry, name.encode(), len(asm.code), asm.body_start, asm.epilogue_start, n_consts,
+                             asm.n_slots, max(1, asm.stats["max_cold"]), asm.n_tmem, ctas, code_off, consts_off)
         blobs.append((code_off, code, consts_off, consts))
     data = bytearray(off)
-    data[0:16] = struct.pack("<8sII", b"B2BLSPRG", 1, len(progs))
+    data[0:16] = struct.pack("<8sII", b"B2BLSPRG", 2, len(progs))
     data[16:16 + len(table)] = table
     for code_off, code, consts_off, consts in blobs:
         data[code_off:code_off + len(code)] = code
