@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200bls.so")
+LIB_PATH = os.environ.get("B200BLS_LIB") or os.path.join(_HERE, "libb200bls.so")
 
 
 class B200BlsError(RuntimeError):

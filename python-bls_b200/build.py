@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 GEN = os.path.join(CSRC, "gen")
 LIB = os.path.join(HERE, "bls_b200", "libb200bls.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-DB200BLS_MUL_CALL"]
 
 
 def _newer(target, deps):

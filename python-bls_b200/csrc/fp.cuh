@@ -304,7 +304,7 @@ FP_DEV void mont_round(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t b
   od[NL - 1] = addc(od[NL - 1], 0);
 }
 
-FP_DEV void fp_mul(fp& r, const fp& a, const fp& b) {
+FP_DEV void fp_mul_inline(fp& r, const fp& a, const fp& b) {
   uint32_t ev[NL], od[NL];
   mont_round_first(ev, od, a.v, b.v[0]);
 #pragma unroll
@@ -321,6 +321,21 @@ FP_DEV void fp_mul(fp& r, const fp& a, const fp& b) {
   t.v[NL - 1] = addc(ev[NL - 1], 0);
   fp_cond_sub_q(r, t);
 }
+
+#if defined(B200BLS_HOSTSIM) || !defined(B200BLS_MUL_CALL)
+FP_DEV void fp_mul(fp& r, const fp& a, const fp& b) { fp_mul_inline(r, a, b); }
+#else
+// ONE copy of the multiplication in the whole kernel: operands and result travel in registers
+// (ptxas: 0 bytes stack).  The interpreter's hot code then fits the instruction cache, which is
+// what limits the number of co-resident warps (icc hit rate 81% -> stalls with 12 warps/SM when
+// every opcode body inlines its own copies; profiles/r1_pairing_c2_vs_c3.txt).
+__device__ __noinline__ fp fp_mul_call(fp a, fp b) {
+  fp r;
+  fp_mul_inline(r, a, b);
+  return r;
+}
+__device__ __forceinline__ void fp_mul(fp& r, const fp& a, const fp& b) { r = fp_mul_call(a, b); }
+#endif
 
 FP_DEV void fp_sqr(fp& r, const fp& a) { fp_mul(r, a, a); }
 

@@ -62,6 +62,7 @@ __device__ __forceinline__ void tm_st4(uint32_t addr, const uint32_t* v) {
 __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+template <bool USE_TMEM>
 struct DevEnv {
   uint4* sm;               // shared workspace, already offset by threadIdx.x
   uint32_t tm_base;        // TMEM address of column 0 in this warp's lane quadrant
@@ -83,8 +84,9 @@ struct DevEnv {
   }
   // the cell index comes from the instruction word: the shared/tensor-memory branch is
   // warp-uniform, as tcgen05.ld/st (.sync.aligned) require
+#define VM_IN_SMEM(c) (!USE_TMEM || (c) < smem_cells)
   __device__ __forceinline__ void ld1(int c, fp& x) {
-    if (c < smem_cells) {
+    if (VM_IN_SMEM(c)) {
       const uint4* q = sm + c * (3 * VM_NT);
 #pragma unroll
       for (int k = 0; k < 3; k++) unpack(x, k, q[k * VM_NT]);
@@ -97,7 +99,7 @@ struct DevEnv {
     }
   }
   __device__ __forceinline__ void st1(int c, const fp& x) {
-    if (c < smem_cells) {
+    if (VM_IN_SMEM(c)) {
       uint4* q = sm + c * (3 * VM_NT);
 #pragma unroll
       for (int k = 0; k < 3; k++) q[k * VM_NT] = pack(x, k);
@@ -108,7 +110,7 @@ struct DevEnv {
     }
   }
   __device__ __forceinline__ void ld2(int c, fp2& x) {
-    if (c < smem_cells) {
+    if (VM_IN_SMEM(c)) {
       const uint4* q = sm + c * (3 * VM_NT);
 #pragma unroll
       for (int k = 0; k < 3; k++) unpack(x.c0, k, q[k * VM_NT]);
@@ -125,7 +127,7 @@ struct DevEnv {
     }
   }
   __device__ __forceinline__ void st2(int c, const fp2& x) {
-    if (c < smem_cells) {
+    if (VM_IN_SMEM(c)) {
       uint4* q = sm + c * (3 * VM_NT);
 #pragma unroll
       for (int k = 0; k < 3; k++) q[k * VM_NT] = pack(x.c0, k);
@@ -234,7 +236,8 @@ struct DevEnv {
   __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
-__device__ __forceinline__ void vm_run_section(DevEnv& env, const uint2* code, int lo, int hi) {
+template <class Env>
+__device__ __forceinline__ void vm_run_section(Env& env, const uint2* code, int lo, int hi) {
   int pc = lo;
   if (pc >= hi) return;
   uint2 ins = __ldg(code + pc);
@@ -251,14 +254,20 @@ __device__ __forceinline__ void vm_run_section(DevEnv& env, const uint2* code, i
   }
 }
 
-__global__ void __launch_bounds__(VM_NT, 3) vm_kernel(const __grid_constant__ VmParams p) {
+// USE_TMEM = false: no tcgen05 instruction in the kernel at all.  (Measured on B200: a kernel
+// that merely CONTAINS tcgen05.alloc holds the SM's allocation permit from CTA launch until it
+// executes relinquish_alloc_permit or exits, which serialises co-resident CTAs -- see
+// tools/experiments/tmem_residency_test.cu.  Hence two instantiations, and the TMEM one always
+// allocates and relinquishes first thing.)
+template <bool USE_TMEM, int MIN_CTAS>
+__global__ void __launch_bounds__(VM_NT, MIN_CTAS) vm_kernel(const __grid_constant__ VmParams p) {
   extern __shared__ uint4 vm_smem[];
   __shared__ uint32_t s_tmem;
   __shared__ int s_blk;
-  DevEnv env;
+  DevEnv<USE_TMEM> env;
   env.smem_cells = p.smem_cells;
   env.tm_base = 0;
-  if (p.tmem_cols) {
+  if (USE_TMEM) {
     // warp 0 allocates this CTA's columns; co-resident CTAs share the SM's 512
     if (threadIdx.x < 32) {
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_tmem);
@@ -314,7 +323,7 @@ __global__ void __launch_bounds__(VM_NT, 3) vm_kernel(const __grid_constant__ Vm
     }
     vm_run_section(env, p.code, lo, hi);
   }
-  if (p.tmem_cols) {
+  if (USE_TMEM) {
     tm_wait_st();
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "python-bls_b200"))
 from bls_b200 import _lib, engine                           # noqa: E402
 
 _lib.init(0)
-n = _lib.lib.b200bls_sm_count() * 256
+n = _lib.lib.b200bls_sm_count() * 128 * _lib.lib.b200bls_get_ctas_per_sm()
 rng = np.random.default_rng(7)
 P = rng.integers(0, 256, size=(n, 96), dtype=np.uint8)
 Q = rng.integers(0, 256, size=(n, 192), dtype=np.uint8)
