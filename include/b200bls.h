@@ -51,7 +51,7 @@ int b200bls_sm_count(void);              /* SMs of the initialised device, 0 if 
 int b200bls_sync(void);                  /* wait for the library stream */
 /* Launch shape: 1 = one 128-thread CTA per SM with 18 Fq2 workspace slots per thread,
  * 2 = two co-resident CTAs per SM with 9 slots each (more latency hiding, more spills to
- * the global cold area).  Default 2 (measured faster, profiles/r1_call2_probe.log), or the environment variable B200BLS_CTAS_PER_SM. */
+ * the global cold area).  Default 3 (measured fastest without register spills), or the environment variable B200BLS_CTAS_PER_SM. */
 /* The library owns 4 CUDA streams.  *_dev entry points enqueue on the stream selected here
  * (default 0); launches on different streams overlap, which removes the tail-wave loss
  * between back-to-back batches.  b200bls_sync() waits for all of them; the timer brackets all

@@ -89,7 +89,7 @@ struct Context {
   std::map<std::string, DevProgram> programs;
   Staging staging[VM_MAX_BUFS];
   uint64_t launches = 0;
-  int ctas_per_sm = 2;   // 1: 18-slot programs, 2: the "#9" variants, two CTAs per SM
+  int ctas_per_sm = 3;   // CTAs of 128 threads per SM (launch shape, see programs/registry.py)
 };
 
 Context g_ctx;

@@ -283,166 +283,125 @@ FP_DEV bool fp_raw_gt(const fp& a, const fp& b) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Multiplication = unreduced 768-bit product (fp_mul_wide) + Montgomery reduction (fp_redc).
+// Montgomery multiplication: r = a * b / R mod q, coarsely integrated operand scanning.
 //
-// Both are "row" algorithms on two interleaved 24-limb accumulators: T = E + O * 2^32, E
-// holds the 64-bit columns at even word positions, O those at odd positions (O[k] has weight
-// 2^(32(k+1))).  A row adds x * y_i * 2^(32 i) for a 12-limb x: its even limbs form one carry
-// chain of six lo/hi pairs into E or O (by the parity of i), its odd limbs a second,
-// independent chain into the other set.  ptxas fuses every lo/hi pair into one
-// IMAD.WIDE.U32.X with a predicate carry and interleaves the chains (3-4 in flight).
-// Splitting product and reduction lets Fq2 arithmetic add / subtract unreduced products and
-// reduce once per coefficient: 3 products + 2 reductions = 744 limb products per Fq2
-// multiplication instead of 900.
+// State T = E + O * 2^32.  E = ev[0..11] holds 64-bit columns at even word positions,
+// O = od[0..11] the columns at odd positions (od[k] has weight 2^(32(k+1))).  One round
+// adds a * b_i and m * q to both sets with four carry chains of six lo/hi pairs each and
+// then divides by 2^32 by *renaming*: the odd set becomes the even set of the next round
+// and the even set, shifted down two words, becomes the odd one.  The word that falls
+// between the two (ev[1]) is folded in by the first add of the next round, whose carry is
+// consumed by the following chain -- the trick known from CGBN / sppark's mont_t.  ptxas
+// fuses every lo/hi pair into one IMAD.WIDE.U32.X with a predicate carry and keeps 3-4 of
+// the chains in flight.
+//
+// Bounds: for a < alpha q, b < beta q the result is < q (0.1016 alpha beta + 1): weakly
+// reduced inputs give < 1.41 q, sums of two (< 4q each) give < 2.63 q; intermediates stay
+// below (alpha + 1) q < 2^384 for alpha <= 8.  No final subtraction.
+//
+// (Tried and rejected, measured on B200: separate 768-bit products + one Montgomery reduction
+// per Fq2 coefficient -- 744 instead of 900 limb products per Fq2 multiplication, but as many
+// instructions in total and less instruction-level parallelism in the reduction rounds:
+// 1.20 M vs 1.27 M pairings/s in the same launch shape.  The kernel is bound by dependent-
+// issue latency, not by the multiply pipe's throughput.)
 // ---------------------------------------------------------------------------------------
-struct fpw {
-  uint32_t v[2 * NL];
-};
+// acc[0..11] (+)= x[j] * y for j = start, start+2, ..., 6 columns; continues an open carry
+template <bool CARRY_IN>
+FP_DEV void mad_row(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+  for (int j = 0; j < NL; j += 2) {
+    if (j == 0 && !CARRY_IN)
+      acc[j] = mad_lo_cc(x[j], y, acc[j]);
+    else
+      acc[j] = madc_lo_cc(x[j], y, acc[j]);
+    acc[j + 1] = madc_hi_cc(x[j], y, acc[j + 1]);
+  }
+}
 
-// acc[s .. s+11] += {x[off], x[off+2], ...} * y as one carry chain; carry out -> acc[s+12]
+// same with the constant modulus as multiplicand; OFF selects even (0) / odd (1) limbs
 template <int OFF>
-FP_DEV void row_chain(uint32_t* acc, int s, const uint32_t* x, uint32_t y) {
+FP_DEV void mad_row_q(uint32_t* acc, uint32_t y) {
 #pragma unroll
   for (int j = 0; j < NL; j += 2) {
     if (j == 0)
-      acc[s + j] = mad_lo_cc(x[j + OFF], y, acc[s + j]);
+      acc[j] = mad_lo_cc(QL(j + OFF), y, acc[j]);
     else
-      acc[s + j] = madc_lo_cc(x[j + OFF], y, acc[s + j]);
-    acc[s + j + 1] = madc_hi_cc(x[j + OFF], y, acc[s + j + 1]);
+      acc[j] = madc_lo_cc(QL(j + OFF), y, acc[j]);
+    acc[j + 1] = madc_hi_cc(QL(j + OFF), y, acc[j + 1]);
   }
-  if (s + NL < 2 * NL) acc[s + NL] = addc(acc[s + NL], 0);
 }
 
-template <int OFF>
-FP_DEV void row_chain_q(uint32_t* acc, int s, uint32_t y) {
+// acc_new[k] = acc[k+2] + x[j]*y columns, i.e. accumulate while shifting down two words;
+// starts with an incoming carry (from the fold of the dropped word)
+FP_DEV void madc_row_rshift(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+  for (int j = 0; j < NL - 2; j += 2) {
+    acc[j] = madc_lo_cc(x[j], y, acc[j + 2]);
+    acc[j + 1] = madc_hi_cc(x[j], y, acc[j + 3]);
+  }
+  acc[NL - 2] = madc_lo_cc(x[NL - 2], y, 0);
+  acc[NL - 1] = madc_hi(x[NL - 2], y, 0);
+}
+
+FP_DEV void mont_round_first(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi) {
 #pragma unroll
   for (int j = 0; j < NL; j += 2) {
-    if (j == 0)
-      acc[s + j] = mad_lo_cc(QL(j + OFF), y, acc[s + j]);
-    else
-      acc[s + j] = madc_lo_cc(QL(j + OFF), y, acc[s + j]);
-    acc[s + j + 1] = madc_hi_cc(QL(j + OFF), y, acc[s + j + 1]);
+    ev[j] = mul_lo(a[j], bi);
+    ev[j + 1] = mul_hi(a[j], bi);
+    od[j] = mul_lo(a[j + 1], bi);
+    od[j + 1] = mul_hi(a[j + 1], bi);
   }
-  if (s + NL < 2 * NL) acc[s + NL] = addc(acc[s + NL], 0);
+  uint32_t m = mul_lo(ev[0], Q_INV_NEG);
+  mad_row_q<1>(od, m);  // no carry out: T < 2^(32*13)
+  mad_row_q<0>(ev, m);
+  od[NL - 1] = addc(od[NL - 1], 0);
 }
 
-// t = a * b, any 384-bit a, b
-FP_DEV void fp_mul_wide_inline(fpw& t, const fp& a, const fp& b) {
-  uint32_t E[2 * NL], O[2 * NL];
+// ev: set that is even-aligned in THIS round; od: last round's even set (od[0] == 0,
+// od[1] is the word to fold, od[2..] become this round's odd columns)
+FP_DEV void mont_round(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi) {
+  ev[0] = add_cc(ev[0], od[1]);
+  madc_row_rshift(od, a + 1, bi);
+  mad_row<false>(ev, a, bi);
+  od[NL - 1] = addc(od[NL - 1], 0);
+  uint32_t m = mul_lo(ev[0], Q_INV_NEG);
+  mad_row_q<1>(od, m);
+  mad_row_q<0>(ev, m);
+  od[NL - 1] = addc(od[NL - 1], 0);
+}
+
+FP_DEV void fp_mul_inline(fp& r, const fp& a, const fp& b) {
+  uint32_t ev[NL], od[NL];
+  mont_round_first(ev, od, a.v, b.v[0]);
 #pragma unroll
-  for (int k = 0; k < 2 * NL; k++) E[k] = O[k] = 0;
-#pragma unroll
-  for (int i = 0; i < NL; i++) {
-    if ((i & 1) == 0) {
-      row_chain<0>(E, i, a.v, b.v[i]);      // even limbs -> even positions i + j
-      row_chain<1>(O, i, a.v, b.v[i]);      // odd limbs  -> odd positions, O index = pos - 1
-    } else {
-      row_chain<0>(O, i - 1, a.v, b.v[i]);  // even limbs -> odd positions i + j
-      row_chain<1>(E, i + 1, a.v, b.v[i]);  // odd limbs  -> even positions i + j
-    }
+  for (int i = 1; i < NL; i += 2) {
+    mont_round(od, ev, a.v, b.v[i]);
+    if (i + 1 < NL) mont_round(ev, od, a.v, b.v[i + 1]);
   }
-  t.v[0] = E[0];
-  t.v[1] = add_cc(E[1], O[0]);
+  // 12 rounds: the last one ran with (od, ev) roles, so `od` was the even-aligned set
+  // (od[0] == 0 now) and `ev` holds the odd columns: T / 2^32 = ev + (od >> one word)
+  fp t;
+  t.v[0] = add_cc(ev[0], od[1]);
 #pragma unroll
-  for (int k = 2; k < 2 * NL - 1; k++) t.v[k] = addc_cc(E[k], O[k - 1]);
-  t.v[2 * NL - 1] = addc(E[2 * NL - 1], O[2 * NL - 2]);
-}
-
-// r = t / R mod q (Montgomery reduction), r < t / R + q.  Callers keep t < 16 q^2, so that
-// r < 2.63 q fits 12 limbs and no intermediate exceeds 768 bits.
-FP_DEV void fp_redc_inline(fp& r, const fpw& t) {
-  uint32_t E[2 * NL], O[2 * NL];
-#pragma unroll
-  for (int k = 0; k < 2 * NL; k++) {
-    E[k] = t.v[k];
-    O[k] = 0;
-  }
-  uint32_t c = 0;  // carry out of the (zeroed) merged limbs below the current one
-#pragma unroll
-  for (int i = 0; i < NL; i++) {
-    uint32_t lo = E[i] + c;
-    if (i > 0) lo += O[i - 1];
-    const uint32_t m = mul_lo(lo, Q_INV_NEG);
-    if ((i & 1) == 0) {
-      row_chain_q<0>(E, i, m);
-      row_chain_q<1>(O, i, m);
-    } else {
-      row_chain_q<0>(O, i - 1, m);
-      row_chain_q<1>(E, i + 1, m);
-    }
-    // merged limb i is now 0 mod 2^32; its carry moves up
-    uint32_t s1 = add_cc(E[i], c);
-    uint32_t k1 = addc(0, 0);
-    uint32_t k2 = 0;
-    if (i > 0) {
-      s1 = add_cc(s1, O[i - 1]);
-      k2 = addc(0, 0);
-    }
-    (void)s1;
-    c = k1 + k2;
-  }
-  fp u;
-  u.v[0] = add_cc(E[NL], c);
-#pragma unroll
-  for (int k = 1; k < NL - 1; k++) u.v[k] = addc_cc(E[NL + k], 0);
-  u.v[NL - 1] = addc(E[2 * NL - 1], 0);
-  r.v[0] = add_cc(u.v[0], O[NL - 1]);
-#pragma unroll
-  for (int k = 1; k < NL - 1; k++) r.v[k] = addc_cc(u.v[k], O[NL - 1 + k]);
-  r.v[NL - 1] = addc(u.v[NL - 1], O[2 * NL - 2]);
-}
-
-FP_DEV void fpw_add(fpw& r, const fpw& a, const fpw& b) {
-  r.v[0] = add_cc(a.v[0], b.v[0]);
-#pragma unroll
-  for (int k = 1; k < 2 * NL - 1; k++) r.v[k] = addc_cc(a.v[k], b.v[k]);
-  r.v[2 * NL - 1] = addc(a.v[2 * NL - 1], b.v[2 * NL - 1]);
-}
-
-FP_DEV void fpw_sub(fpw& r, const fpw& a, const fpw& b) {
-  r.v[0] = sub_cc(a.v[0], b.v[0]);
-#pragma unroll
-  for (int k = 1; k < 2 * NL - 1; k++) r.v[k] = subc_cc(a.v[k], b.v[k]);
-  r.v[2 * NL - 1] = subc(a.v[2 * NL - 1], b.v[2 * NL - 1]);
-}
-
-// r = a + 4 q^2 (keeps a following subtraction of a product < 4 q^2 non-negative)
-FP_DEV void fpw_add_4qq(fpw& r, const fpw& a) {
-  r.v[0] = add_cc(a.v[0], QQ4L(0));
-#pragma unroll
-  for (int k = 1; k < 2 * NL - 1; k++) r.v[k] = addc_cc(a.v[k], QQ4L(k));
-  r.v[2 * NL - 1] = addc(a.v[2 * NL - 1], QQ4L(2 * NL - 1));
+  for (int i = 1; i < NL - 1; i++) t.v[i] = addc_cc(ev[i], od[i + 1]);
+  t.v[NL - 1] = addc(ev[NL - 1], 0);
+  r = t;  // < 1.41 q for weakly reduced inputs (< 2.63 q for inputs < 4q): no final subtraction
 }
 
 #if defined(B200BLS_HOSTSIM) || !defined(B200BLS_MUL_CALL)
-FP_DEV void fp_mul_wide(fpw& t, const fp& a, const fp& b) { fp_mul_wide_inline(t, a, b); }
-FP_DEV void fp_redc(fp& r, const fpw& t) { fp_redc_inline(r, t); }
+FP_DEV void fp_mul(fp& r, const fp& a, const fp& b) { fp_mul_inline(r, a, b); }
 #else
-// ONE copy of the product and ONE of the reduction in the whole kernel: operands and results
-// travel in registers (ptxas: 0 bytes stack).  The interpreter's hot code then fits the
-// instruction cache, which is what limits the number of co-resident warps (icc hit rate 81%
-// and `no_instruction` stalls with 12 warps/SM when every opcode body inlines its own copies).
-__device__ __noinline__ fpw fp_mul_wide_call(fp a, fp b) {
-  fpw t;
-  fp_mul_wide_inline(t, a, b);
-  return t;
-}
-__device__ __noinline__ fp fp_redc_call(fpw t) {
+// ONE copy of the multiplication in the whole kernel: operands and result travel in registers
+// (ptxas: 0 bytes stack).  The interpreter's hot code then fits the instruction cache, which is
+// what limits the number of co-resident warps (icc hit rate 81% and `no_instruction` stalls
+// with 12 warps/SM when every opcode body inlines its own copies).
+__device__ __noinline__ fp fp_mul_call(fp a, fp b) {
   fp r;
-  fp_redc_inline(r, t);
+  fp_mul_inline(r, a, b);
   return r;
 }
-__device__ __forceinline__ void fp_mul_wide(fpw& t, const fp& a, const fp& b) { t = fp_mul_wide_call(a, b); }
-__device__ __forceinline__ void fp_redc(fp& r, const fpw& t) { r = fp_redc_call(t); }
+__device__ __forceinline__ void fp_mul(fp& r, const fp& a, const fp& b) { r = fp_mul_call(a, b); }
 #endif
-
-// r = a * b / R mod q: weakly reduced in -> r < 1.41 q (weakly reduced), no final subtraction.
-// b may be ANY 384-bit value when a < q (used by the byte loaders): r < 2q still.
-FP_DEV void fp_mul(fp& r, const fp& a, const fp& b) {
-  fpw t;
-  fp_mul_wide(t, a, b);
-  fp_redc(r, t);
-}
 
 FP_DEV void fp_sqr(fp& r, const fp& a) { fp_mul(r, a, a); }
 
@@ -461,39 +420,28 @@ FP_DEV void fp2_neg(fp2& r, const fp2& a) {
   fp_neg(r.c0, a.c0);
   fp_neg(r.c1, a.c1);
 }
-// Karatsuba on unreduced products, one reduction per coefficient (fields_t.py:157-161 uses 4
-// full multiplications): c0 = a0 b0 - a1 b1, c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1.
-// Bounds for weakly reduced inputs: products < 4 q^2, the sum product < 16 q^2;
-// c0 + 4 q^2 < 8 q^2 -> r.c0 < 1.81 q;  c1 < 16 q^2 -> < 2.63 q -> one conditional - 2q.
+// Karatsuba, 3 base multiplications (fields_t.py:157-161 uses 4).  The operand sums are left
+// unreduced (< 4q), so their product is < 2.63 q and takes one conditional subtraction of 2q.
 FP_DEV void fp2_mul(fp2& r, const fp2& a, const fp2& b) {
-  fp sa, sb;
-  fpw t0, t1, t2;
+  fp sa, sb, t0, t1, t2;
   fp_add_raw(sa, a.c0, a.c1);
   fp_add_raw(sb, b.c0, b.c1);
-  fp_mul_wide(t0, a.c0, b.c0);
-  fp_mul_wide(t1, a.c1, b.c1);
-  fp_mul_wide(t2, sa, sb);
-  fpw_sub(t2, t2, t0);
-  fpw_sub(t2, t2, t1);          // a0 b1 + a1 b0 >= 0
-  fpw_add_4qq(t0, t0);
-  fpw_sub(t0, t0, t1);
-  fp_redc(r.c0, t0);
-  fp c1;
-  fp_redc(c1, t2);
-  fp_cond_sub_2q(r.c1, c1);
+  fp_mul(t0, a.c0, b.c0);
+  fp_mul(t1, a.c1, b.c1);
+  fp_mul(t2, sa, sb);
+  fp_cond_sub_2q(t2, t2);
+  fp_sub(r.c0, t0, t1);
+  fp_sub(t2, t2, t0);
+  fp_sub(r.c1, t2, t1);
 }
-// (a0 + a1)(a0 - a1 + 2q), (2 a0) a1
+// (a0 + a1)(a0 - a1 + 2q), (2 a0) a1 with unreduced sums
 FP_DEV void fp2_sqr(fp2& r, const fp2& a) {
-  fp s, d, e;
-  fpw t;
+  fp s, d, e, c0;
   fp_add_raw(s, a.c0, a.c1);        // < 4q
   fp_sub_raw_2q(d, a.c0, a.c1);     // in (0, 4q)
   fp_add_raw(e, a.c0, a.c0);        // < 4q
-  fp_mul_wide(t, s, d);             // < 16 q^2
-  fp c0;
-  fp_redc(c0, t);
-  fp_mul_wide(t, e, a.c1);          // < 8 q^2
-  fp_redc(r.c1, t);
+  fp_mul(c0, s, d);                 // < 2.63 q
+  fp_mul(r.c1, e, a.c1);            // < 1.82 q
   fp_cond_sub_2q(r.c0, c0);
 }
 // times xi = 1 + u  (fields_t.py:113-116)
