@@ -104,6 +104,10 @@ int b200bls_field_op_batch_dev(int level, int op, const void* a, const void* b, 
 /* fq_miller_loop + fq12_final_exp per pair (fields_t.py:1091-1128; pairing.py:76-81
  * ate_pairing).  out: n x 576. */
 int b200bls_pairing_batch(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n);
+/* Asynchronous host-buffer form: enqueues H2D copy, kernel and D2H copy on the selected stream
+ * and returns; call b200bls_sync() before reading `out`.  Use pinned host buffers
+ * (b200bls_host_alloc) and alternate b200bls_set_stream() to overlap consecutive batches. */
+int b200bls_pairing_batch_async(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n);
 int b200bls_pairing_batch_dev(const void* P, const void* Q, void* out, size_t n);
 /* fq12_final_exp (fields_t.py:1124-1128; pairing.py:68-73).  in/out: n x 576. */
 int b200bls_final_exp_batch(const uint8_t* in, uint8_t* out, size_t n);

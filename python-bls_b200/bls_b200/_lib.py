@@ -46,6 +46,7 @@ def _load():
         "b200bls_field_op_batch": (i32, [i32, i32, vp, vp, vp, sz]),
         "b200bls_field_op_batch_dev": (i32, [i32, i32, vp, vp, vp, sz]),
         "b200bls_pairing_batch": (i32, [vp, vp, vp, sz]),
+        "b200bls_pairing_batch_async": (i32, [vp, vp, vp, sz]),
         "b200bls_pairing_batch_dev": (i32, [vp, vp, vp, sz]),
         "b200bls_final_exp_batch": (i32, [vp, vp, sz]),
         "b200bls_final_exp_batch_dev": (i32, [vp, vp, sz]),

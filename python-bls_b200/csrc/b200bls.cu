@@ -76,6 +76,7 @@ struct StreamCtx {
   int* counters = nullptr;   // ring of item-block counters, one per launch in flight
   unsigned counter_pos = 0;
   Staging scratch[6];        // device-side intermediates of multi-stage entry points
+  Staging staging[VM_MAX_BUFS];  // device copies of the caller's host buffers
 };
 constexpr int N_COUNTERS = 256;
 
@@ -87,7 +88,6 @@ struct Context {
   int cur = 0;               // stream used by the calling API function (b200bls_set_stream)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::map<std::string, DevProgram> programs;
-  Staging staging[VM_MAX_BUFS];
   uint64_t launches = 0;
   int ctas_per_sm = 3;   // CTAs of 128 threads per SM (launch shape, see programs/registry.py)
 };
@@ -99,7 +99,7 @@ StreamCtx& cur() { return g_ctx.sc[g_ctx.cur]; }
 #define STREAM (cur().stream)
 
 int ensure_buf(Staging& s, size_t bytes);
-int ensure_staging(int i, size_t bytes) { return ensure_buf(g_ctx.staging[i], bytes); }
+int ensure_staging(int i, size_t bytes) { return ensure_buf(cur().staging[i], bytes); }
 int ensure_scratch(int i, size_t bytes) { return ensure_buf(cur().scratch[i], bytes); }
 
 int ensure_buf(Staging& s, size_t bytes) {
@@ -186,44 +186,29 @@ struct HostBuf {
   size_t stride;    // bytes per item
 };
 
-// copy inputs up, run, copy outputs back, synchronise.  Large batches are cut into chunks
-// that go to alternating streams: the H2D copy of one chunk overlaps the kernel of another,
-// and the dynamically scheduled CTAs of consecutive chunks fill each other's tail waves.
-int run_host(const char* name, size_t n, const HostBuf* hb, int n_bufs) {
+// copy inputs up, run, copy outputs back on the selected stream; synchronise unless the caller
+// asked for the asynchronous form (then b200bls_sync() must precede any use of the outputs and
+// the host buffers should be pinned so that the copies really overlap other streams' kernels)
+int run_host(const char* name, size_t n, const HostBuf* hb, int n_bufs, bool sync = true) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "b200bls_init() has not succeeded");
   const DevProgram* pr = find_program(name);
   if (!pr) return B200BLS_E_PROGRAM;
   if (n == 0) return 0;
+  VmBuf bufs[VM_MAX_BUFS];
+  memset(bufs, 0, sizeof(bufs));
   for (int i = 0; i < n_bufs; i++) {
     int rc = ensure_staging(i, hb[i].stride * n);
     if (rc) return rc;
+    bufs[i].ptr = (unsigned char*)cur().staging[i].ptr;
+    bufs[i].stride = (long long)hb[i].stride;
+    if (hb[i].in) CU(cudaMemcpyAsync(bufs[i].ptr, hb[i].in, hb[i].stride * n, cudaMemcpyHostToDevice, STREAM));
   }
-  const size_t wave = (size_t)g_ctx.sm_count * pr->ctas * VM_NT;
-  size_t n_chunks = n >= 2 * wave ? 4 : 1;
-  size_t per = ((n + n_chunks - 1) / n_chunks + VM_NT - 1) / VM_NT * VM_NT;
-  const int home = g_ctx.cur;
-  int rc = 0;
-  for (size_t c = 0, lo = 0; lo < n && !rc; c++, lo += per) {
-    size_t cnt = n - lo < per ? n - lo : per;
-    g_ctx.cur = (home + (int)(c % 2)) % N_STREAMS;
-    VmBuf bufs[VM_MAX_BUFS];
-    memset(bufs, 0, sizeof(bufs));
-    for (int i = 0; i < n_bufs; i++) {
-      bufs[i].ptr = (unsigned char*)g_ctx.staging[i].ptr + lo * hb[i].stride;
-      bufs[i].stride = (long long)hb[i].stride;
-      if (hb[i].in)
-        CU(cudaMemcpyAsync(bufs[i].ptr, (const unsigned char*)hb[i].in + lo * hb[i].stride, hb[i].stride * cnt,
-                           cudaMemcpyHostToDevice, STREAM));
-    }
-    rc = launch_program(*pr, cnt, bufs, n_bufs);
-    for (int i = 0; i < n_bufs && !rc; i++)
-      if (hb[i].out)
-        CU(cudaMemcpyAsync((unsigned char*)hb[i].out + lo * hb[i].stride, bufs[i].ptr, hb[i].stride * cnt,
-                           cudaMemcpyDeviceToHost, STREAM));
-  }
-  g_ctx.cur = home;
-  for (int k = 0; k < 2; k++) CU(cudaStreamSynchronize(g_ctx.sc[(home + k) % N_STREAMS].stream));
-  return rc;
+  int rc = launch_program(*pr, n, bufs, n_bufs);
+  if (rc) return rc;
+  for (int i = 0; i < n_bufs; i++)
+    if (hb[i].out) CU(cudaMemcpyAsync(hb[i].out, bufs[i].ptr, hb[i].stride * n, cudaMemcpyDeviceToHost, STREAM));
+  if (sync) CU(cudaStreamSynchronize(STREAM));
+  return 0;
 }
 
 struct DevBuf {
@@ -379,7 +364,7 @@ int compress_dev(bool g2, const void* aff, void* out, size_t n) {
 }
 
 // host-pointer wrapper around a device pipeline: ins/outs are (host ptr, bytes) pairs staged
-// through g_ctx.staging[0..]
+// through cur().staging[0..]
 struct HostIO {
   const void* in;
   void* out;
@@ -393,7 +378,7 @@ int with_staging(const HostIO* io, int n_io, F&& body) {
   for (int i = 0; i < n_io; i++) {
     int rc = ensure_staging(i, io[i].bytes ? io[i].bytes : 1);
     if (rc) return rc;
-    dev[i] = g_ctx.staging[i].ptr;
+    dev[i] = cur().staging[i].ptr;
     if (io[i].in && io[i].bytes) CU(cudaMemcpyAsync(dev[i], io[i].in, io[i].bytes, cudaMemcpyHostToDevice, STREAM));
   }
   int rc = body(dev);
@@ -495,13 +480,13 @@ void b200bls_shutdown(void) {
     cudaFree(kv.second.consts);
   }
   c.programs.clear();
-  for (auto& s : c.staging) {
-    if (s.ptr) cudaFree(s.ptr);
-    s.ptr = nullptr;
-    s.cap = 0;
-  }
   for (auto& sc : c.sc) {
     for (auto& s : sc.scratch) {
+      if (s.ptr) cudaFree(s.ptr);
+      s.ptr = nullptr;
+      s.cap = 0;
+    }
+    for (auto& s : sc.staging) {
       if (s.ptr) cudaFree(s.ptr);
       s.ptr = nullptr;
       s.cap = 0;
@@ -664,6 +649,13 @@ int b200bls_pairing_batch(const uint8_t* P, const uint8_t* Q, uint8_t* out, size
   if (!P || !Q || !out) return fail(B200BLS_E_ARG, "null buffer");
   HostBuf hb[3] = {{P, nullptr, 96}, {Q, nullptr, 192}, {nullptr, out, 576}};
   return run_host("pairing", n, hb, 3);
+}
+
+int b200bls_pairing_batch_async(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!P || !Q || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[3] = {{P, nullptr, 96}, {Q, nullptr, 192}, {nullptr, out, 576}};
+  return run_host("pairing", n, hb, 3, false);
 }
 
 int b200bls_pairing_batch_dev(const void* P, const void* Q, void* out, size_t n) {
@@ -851,10 +843,10 @@ int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8
   if ((rc = ensure_staging(1, 32 * n + 1))) return rc;
   if ((rc = ensure_staging(2, 192 * (n + 1)))) return rc;
   if ((rc = ensure_staging(3, 576 * 2))) return rc;
-  uint8_t* dP = (uint8_t*)g_ctx.staging[0].ptr;
-  uint8_t* dM = (uint8_t*)g_ctx.staging[1].ptr;
-  uint8_t* dQ = (uint8_t*)g_ctx.staging[2].ptr;
-  uint8_t* dF = (uint8_t*)g_ctx.staging[3].ptr;
+  uint8_t* dP = (uint8_t*)cur().staging[0].ptr;
+  uint8_t* dM = (uint8_t*)cur().staging[1].ptr;
+  uint8_t* dQ = (uint8_t*)cur().staging[2].ptr;
+  uint8_t* dF = (uint8_t*)cur().staging[3].ptr;
   CU(cudaMemcpyAsync(dP, kNegG1, 96, cudaMemcpyHostToDevice, STREAM));
   CU(cudaMemcpyAsync(dQ, sig, 192, cudaMemcpyHostToDevice, STREAM));
   if (n) {
