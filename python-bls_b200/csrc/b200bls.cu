@@ -153,9 +153,7 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   p.tmem_cols = pr.n_tmem == 0 ? 0 : (pr.n_tmem * 24 <= 128 ? 128 : (pr.n_tmem * 24 <= 256 ? 256 : 512));
   for (int i = 0; i < n_bufs && i < VM_MAX_BUFS; i++) p.bufs[i] = bufs[i];
   size_t smem = (size_t)pr.n_slots * 2 * 3 * sizeof(uint4) * VM_NT;
-  if (p.tmem_cols && pr.ctas >= 4)
-    vm_kernel<true, 4><<<grid, VM_NT, smem, sc.stream>>>(p);   // <= 128 registers
-  else if (p.tmem_cols)
+  if (p.tmem_cols)
     vm_kernel<true, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
   else
     vm_kernel<false, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
@@ -431,7 +429,6 @@ int b200bls_init(int device) {
   CU(cudaEventCreate(&c.ev1));
   CU(cudaFuncSetAttribute(vm_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   CU(cudaFuncSetAttribute(vm_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  CU(cudaFuncSetAttribute(vm_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   // parse the embedded program blob
   const unsigned char* blob = _binary_programs_bin_start;
   size_t blob_len = (size_t)(_binary_programs_bin_end - _binary_programs_bin_start);
@@ -464,7 +461,7 @@ int b200bls_init(int device) {
     c.programs[nm] = dp;
   }
   const char* env = getenv("B200BLS_CTAS_PER_SM");
-  if (env && env[0] >= '1' && env[0] <= '4') c.ctas_per_sm = env[0] - '0';
+  if (env && env[0] >= '1' && env[0] <= '3') c.ctas_per_sm = env[0] - '0';
   c.device = device;
   c.ready = true;
   return 0;
@@ -508,7 +505,7 @@ int b200bls_sm_count(void) { return g_ctx.ready ? g_ctx.sm_count : 0; }
 
 int b200bls_set_ctas_per_sm(int n) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (n < 1 || n > 4) return fail(B200BLS_E_ARG, "ctas_per_sm must be 1..4");
+  if (n < 1 || n > 3) return fail(B200BLS_E_ARG, "ctas_per_sm must be 1, 2 or 3");
   g_ctx.ctas_per_sm = n;
   return 0;
 }

@@ -16,46 +16,65 @@
 
 namespace b200bls {
 
+#define B200BLS_SHA_K                                                                              \
+  {0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, \
+   0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, \
+   0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, \
+   0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, \
+   0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, \
+   0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, \
+   0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, \
+   0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2}
+
+#ifdef B200BLS_HOSTSIM
+static const uint32_t kShaK[64] = B200BLS_SHA_K;
+#define SHA_K(i) kShaK[i]
+#else
+// compile-time immediates after full unrolling: no table in memory, no local array
+__host__ __device__ __forceinline__ constexpr uint32_t sha_k(int i) {
+  constexpr uint32_t t[64] = B200BLS_SHA_K;
+  return t[i];
+}
+#define SHA_K(i) sha_k(i)
+#endif
+
 SHA_HD uint32_t sha_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
 // one compression of a single padded block holding `h` (32 bytes), a 7-byte label and one
-// suffix byte; digest written big-endian to out[0..31]
+// suffix byte; digest written big-endian to out[0..31].  The message schedule is a rolling
+// 16-word window and every loop is fully unrolled, so everything lives in registers.
 SHA_HD void sha256_h_label(const uint8_t* h, int j, int k, int suffix, uint8_t* out) {
-  const uint32_t K[64] = {
-      0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
-      0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
-      0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
-      0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
-      0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
-      0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
-      0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
-      0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
-  uint32_t w[64];
+  uint32_t w[16];
+#pragma unroll
   for (int i = 0; i < 8; i++)
     w[i] = ((uint32_t)h[4 * i] << 24) | ((uint32_t)h[4 * i + 1] << 16) | ((uint32_t)h[4 * i + 2] << 8) | h[4 * i + 3];
-  // label "G2_j_ck" then the suffix byte, then 0x80 padding
+  // label "G2_j_ck" then the suffix byte, then 0x80 padding and the bit length (40 bytes)
   w[8] = ((uint32_t)'G' << 24) | ((uint32_t)'2' << 16) | ((uint32_t)'_' << 8) | (uint32_t)('0' + j);
   w[9] = ((uint32_t)'_' << 24) | ((uint32_t)'c' << 16) | ((uint32_t)('0' + k) << 8) | (uint32_t)suffix;
   w[10] = 0x80000000u;
-  for (int i = 11; i < 15; i++) w[i] = 0;
+  w[11] = w[12] = w[13] = w[14] = 0;
   w[15] = 40 * 8;
-  for (int i = 16; i < 64; i++) {
-    uint32_t s0 = sha_rotr(w[i - 15], 7) ^ sha_rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
-    uint32_t s1 = sha_rotr(w[i - 2], 17) ^ sha_rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
-    w[i] = w[i - 16] + s0 + w[i - 7] + s1;
-  }
-  uint32_t st[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
-  uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], hh = st[7];
+  uint32_t a = 0x6a09e667, b = 0xbb67ae85, c = 0x3c6ef372, d = 0xa54ff53a;
+  uint32_t e = 0x510e527f, f = 0x9b05688c, g = 0x1f83d9ab, hh = 0x5be0cd19;
+#pragma unroll
   for (int i = 0; i < 64; i++) {
+    if (i >= 16) {
+      uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+      uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+      uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+      w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+    }
     uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
     uint32_t ch = (e & f) ^ (~e & g);
-    uint32_t t1 = hh + S1 + ch + K[i] + w[i];
+    uint32_t t1 = hh + S1 + ch + SHA_K(i) + w[i & 15];
     uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
     uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
     uint32_t t2 = S0 + mj;
     hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
   }
-  uint32_t r[8] = {st[0] + a, st[1] + b, st[2] + c, st[3] + d, st[4] + e, st[5] + f, st[6] + g, st[7] + hh};
+  const uint32_t r[8] = {0x6a09e667 + a, 0xbb67ae85 + b, 0x3c6ef372 + c, 0xa54ff53a + d,
+                         0x510e527f + e, 0x9b05688c + f, 0x1f83d9ab + g, 0x5be0cd19 + hh};
+#pragma unroll
   for (int i = 0; i < 8; i++) {
     out[4 * i] = (uint8_t)(r[i] >> 24);
     out[4 * i + 1] = (uint8_t)(r[i] >> 16);

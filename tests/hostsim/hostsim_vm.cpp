@@ -177,3 +177,13 @@ extern "C" int hs_vm_run(const uint32_t* code, int n_ins, int body_start, int ep
   run(epi_start, n_ins, iters > 0 ? iters - 1 : 0);
   return 0;
 }
+
+#include "../../python-bls_b200/csrc/sha256.cuh"
+// SHA stage of hash-to-G2 on the host (same function the CUDA kernel runs per thread)
+extern "C" void hs_sha_stage(const uint8_t* hashes, uint8_t* out, long n) {
+  for (long item = 0; item < n; item++)
+    for (int sub = 0; sub < 8; sub++) {
+      int j = sub >> 2, k = (sub >> 1) & 1, suffix = sub & 1;
+      sha256_h_label(hashes + item * 32, j, k, suffix, out + item * 256 + (j * 2 + k) * 64 + suffix * 32);
+    }
+}

@@ -1,0 +1,124 @@
+"""CPU checks of the DEVICE code paths: the assembled VM programs run on the host build of the
+interpreter (tests/hostsim: csrc/fp.cuh + vm_exec.cuh with every PTX instruction emulated, the
+kernel's cell / cold / Tensor-Memory-slot layouts) and must reproduce the golden vectors.  This
+is what lets formulas, the allocator and the limb arithmetic be validated without a GPU."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import bls_oracle as O
+import hostsim
+from conftest import load_golden
+
+from bls_b200.programs import curve, fieldops, hashg2, pairing, registry
+
+
+def _pq(cases):
+    P = b"".join(bytes.fromhex(c["p"]["x"]) + bytes.fromhex(c["p"]["y"]) for c in cases)
+    Q = b"".join(bytes.fromhex(c["q"]["x"]) + bytes.fromhex(c["q"]["y"]) for c in cases)
+    return np.frombuffer(P, dtype=np.uint8).copy(), np.frombuffer(Q, dtype=np.uint8).copy()
+
+
+@pytest.mark.parametrize("ctas", sorted(registry.SHAPES))
+def test_pairing_program_every_launch_shape(ctas):
+    n_slots, n_tmem = registry.SHAPES[ctas]
+    g = load_golden("pairing_kat.json")
+    cases = g["pairs"][:5] + g["degenerate"]
+    asm = pairing.build_pairing().assemble(n_slots, n_cold=4096, n_tmem=n_tmem)
+    P, Q = _pq(cases)
+    out = np.zeros(576 * len(cases), dtype=np.uint8)
+    hostsim.run(asm, {0: P, 1: Q, 2: out}, {0: 96, 1: 192, 2: 576}, len(cases), n_blocks=2, nt=3)
+    raw = out.tobytes()
+    for i, c in enumerate(cases):
+        assert raw[576 * i:576 * (i + 1)].hex() == c["out"], (ctas, i)
+
+
+def test_sha_stage_matches_hashlib():
+    lib = hostsim.lib()
+    hs = b"".join(O.hash256(bytes([i])) for i in range(5))
+    out = np.zeros(256 * 5, dtype=np.uint8)
+    lib.hs_sha_stage(hs, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(5))
+    raw = out.tobytes()
+    for i in range(5):
+        h = hs[32 * i:32 * (i + 1)]
+        want = b"".join(O.hash512(h + b"G2_" + j + b"_c" + k) for j in (b"0", b"1") for k in (b"0", b"1"))
+        assert raw[256 * i:256 * (i + 1)] == want
+
+
+def test_hash_and_verify_programs():
+    g = load_golden("hash_kat.json")
+    cases = g["hash_to_g2_prehashed"][:6]
+    lib = hostsim.lib()
+    hs = b"".join(bytes.fromhex(c["h"]) for c in cases)
+    sha = np.zeros(256 * len(cases), dtype=np.uint8)
+    lib.hs_sha_stage(hs, sha.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(len(cases)))
+    asm = hashg2.build_hash_to_g2().assemble(6, n_cold=4096, n_tmem=5)
+    H = np.zeros(192 * len(cases), dtype=np.uint8)
+    hostsim.run(asm, {0: sha, 1: H}, {0: 256, 1: 192}, len(cases), n_blocks=1, nt=4)
+    raw = H.tobytes()
+    for i, c in enumerate(cases):
+        assert raw[192 * i:192 * (i + 1)].hex() == c["out"]["x"] + c["out"]["y"], i
+    # verification core on the reference's own signature vectors
+    sg = load_golden("sig_kat.json")
+    tab = sg["verify_table"][:4]
+
+    def ser1(p):
+        return p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+
+    def ser2(p):
+        return b"".join(c.to_bytes(48, "big") for c in (p[0][0], p[0][1], p[1][0], p[1][1]))
+    pk = np.frombuffer(b"".join(ser1(O.g1_deserialize(bytes.fromhex(t["pk"]))) for t in tab), dtype=np.uint8).copy()
+    Hm = np.frombuffer(b"".join(ser2(O.hash_to_g2_prehashed(bytes.fromhex(t["h"]))) for t in tab), dtype=np.uint8).copy()
+    sig = np.frombuffer(b"".join(ser2(O.g2_deserialize(bytes.fromhex(t["sig"]))) for t in tab), dtype=np.uint8).copy()
+    ok = np.full(len(tab), 9, dtype=np.uint8)
+    asm = pairing.build_verify_pair().assemble(9, n_cold=4096, n_tmem=10)
+    hostsim.run(asm, {0: pk, 1: Hm, 2: sig, 3: ok}, {0: 96, 1: 192, 2: 192, 3: 1}, len(tab), n_blocks=1, nt=4)
+    assert [bool(x) for x in ok] == [t["ok"] for t in tab]
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_sum_programs_with_skipped_and_executed_regions(g2):
+    """two-pass point sums incl. P + P, P + (-P), infinity; SKIPZ regions skipped and not"""
+    G = O.G2 if g2 else O.G1
+    w = 192 if g2 else 96
+
+    def ser(p):
+        if g2:
+            return b"".join(c.to_bytes(48, "big") for c in (p[0][0], p[0][1], p[1][0], p[1][1]))
+        return p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+    pts = [O.aff_mul(k, G) for k in (3, 5, 7, 11, 13)]
+    plist = pts + [pts[1], pts[1], O.aff_neg(pts[2])]
+    data = b"".join(ser(p) for p in plist) + bytes(w)
+    n = len(data) // w
+    a1 = curve.build_sum_pass1(g2)().assemble(18)
+    a2 = curve.build_sum_pass2(g2)().assemble(18)
+    want = ser((O.g2_sum if g2 else O.g1_sum)(plist))
+    for honor in (True, False):
+        nb = 2
+        raw = np.zeros((3 if g2 else 2) * 6 * nb * 16, dtype=np.uint8)
+        hostsim.run(a1, {0: np.frombuffer(data, dtype=np.uint8).copy(), 1: raw}, {0: w, 1: nb}, n,
+                    n_blocks=nb, nt=128, honor_skips=honor)
+        out = np.zeros(w, dtype=np.uint8)
+        hostsim.run(a2, {0: raw, 1: out}, {0: nb, 1: w}, nb, n_blocks=1, nt=128, honor_skips=honor)
+        assert out.tobytes() == want
+
+
+def test_field_programs_on_weakly_reduced_edge_values():
+    """operands 0, 1, q-1 and values >= q on input (reduced on load): mul / inv / sub at level 12"""
+    import random
+    rnd = random.Random(3)
+    Q = O.Q
+    vals = [(0,) * 12, (1,) + (0,) * 11, (Q - 1,) * 12] + [tuple(rnd.randrange(Q) for _ in range(12)) for _ in range(3)]
+
+    def ser(e):
+        return b"".join(int(c).to_bytes(48, "big") for c in e)
+    a = np.frombuffer(b"".join(ser(v) for v in vals), dtype=np.uint8).copy()
+    b = np.frombuffer(b"".join(ser(v) for v in reversed(vals)), dtype=np.uint8).copy()
+    for op, fn in (("mul", O.f12_mul), ("sub", O.f12_sub)):
+        asm = fieldops.build_field_op(12, op)().assemble(6, n_cold=4096, n_tmem=5)
+        out = np.zeros(576 * len(vals), dtype=np.uint8)
+        hostsim.run(asm, {0: a, 1: b, 2: out}, {0: 576, 1: 576, 2: 576}, len(vals), n_blocks=1, nt=2)
+        raw = out.tobytes()
+        for i, v in enumerate(vals):
+            assert raw[576 * i:576 * (i + 1)] == ser(fn(v, vals[len(vals) - 1 - i])), (op, i)

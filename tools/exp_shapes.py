@@ -12,7 +12,7 @@ from bls_b200 import _lib, engine                           # noqa: E402
 
 _lib.init(0)
 sm = _lib.lib.b200bls_sm_count()
-n = sm * 128 * 12
+n = sm * 128 * 6
 rng = np.random.default_rng(7)
 P = rng.integers(0, 256, size=(n, 96), dtype=np.uint8)
 Q = rng.integers(0, 256, size=(n, 192), dtype=np.uint8)
@@ -21,7 +21,7 @@ Q[:, ::48] &= 0x0f
 dP, dQ, dO = engine.DeviceBuffer(96 * n).upload(P), engine.DeviceBuffer(192 * n).upload(Q), engine.DeviceBuffer(576 * n)
 progs = sys.argv[1:] or ["pairing"]
 for prog in progs:
-    for ctas in (1, 2, 3, 4):
+    for ctas in (1, 2, 3):
         _lib.check(_lib.lib.b200bls_set_ctas_per_sm(ctas))
         best = 1e9
         for _ in range(3):
