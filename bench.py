@@ -167,6 +167,7 @@ def run_gpu(args, rank, world, dist):
     from bls_b200._lib import check, lib
     local = int(os.environ.get("LOCAL_RANK", "0"))
     _lib.init(local)
+    check(lib.b200bls_set_ctas_per_sm(3))      # throughput shape: batches overlap on two streams
     n = BATCH
     # --- inputs: NSETS rotating buffer sets so the working set (NSETS * 56.6 MB) exceeds the
     # 126 MB L2 between timed iterations

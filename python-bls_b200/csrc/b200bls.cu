@@ -89,7 +89,7 @@ struct Context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::map<std::string, DevProgram> programs;
   uint64_t launches = 0;
-  int ctas_per_sm = 3;   // CTAs of 128 threads per SM (launch shape, see programs/registry.py)
+  int ctas_per_sm = 0;   // launch shape: CTAs of 128 threads per SM (programs/registry.py); 0 = auto
 };
 
 Context g_ctx;
@@ -162,14 +162,34 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   return 0;
 }
 
-const DevProgram* find_program(const char* base) {
+// Auto shape for an isolated batch of n items: more CTAs per SM raise throughput but also the
+// latency of one pass (measured pairing pass: 1 : 1.3 : 1.85 for 1 : 2 : 3 CTAs/SM), so the best
+// shape minimises passes x latency.  Pipelines that keep several batches in flight (bench.py)
+// select 3 explicitly.
+int auto_ctas(size_t n) {
+  static const double kLat[4] = {0, 1.0, 1.3, 1.85};
+  int best = 1;
+  double best_cost = 1e300;
+  for (int c = 1; c <= 3; c++) {
+    size_t cap = (size_t)g_ctx.sm_count * VM_NT * c;
+    double cost = (double)((n + cap - 1) / cap) * kLat[c];
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+
+const DevProgram* find_program(const char* base, size_t n_items = 0) {
   // "<name>@<ctas>": the configured shape, else the nearest one with fewer CTAs per SM
   std::string name(base);
   if (name.find('@') != std::string::npos) {
     auto it = g_ctx.programs.find(name);
     if (it != g_ctx.programs.end()) return &it->second;
   } else {
-    for (int c = g_ctx.ctas_per_sm; c >= 1; c--) {
+    int want = g_ctx.ctas_per_sm > 0 ? g_ctx.ctas_per_sm : auto_ctas(n_items ? n_items : 1);
+    for (int c = want; c >= 1; c--) {
       auto it = g_ctx.programs.find(name + "@" + std::to_string(c));
       if (it != g_ctx.programs.end()) return &it->second;
     }
@@ -189,7 +209,7 @@ struct HostBuf {
 // the host buffers should be pinned so that the copies really overlap other streams' kernels)
 int run_host(const char* name, size_t n, const HostBuf* hb, int n_bufs, bool sync = true) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "b200bls_init() has not succeeded");
-  const DevProgram* pr = find_program(name);
+  const DevProgram* pr = find_program(name, n);
   if (!pr) return B200BLS_E_PROGRAM;
   if (n == 0) return 0;
   VmBuf bufs[VM_MAX_BUFS];
@@ -216,7 +236,7 @@ struct DevBuf {
 
 int run_dev(const char* name, size_t n, const DevBuf* db, int n_bufs) {
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "b200bls_init() has not succeeded");
-  const DevProgram* pr = find_program(name);
+  const DevProgram* pr = find_program(name, n);
   if (!pr) return B200BLS_E_PROGRAM;
   if (n == 0) return 0;
   VmBuf bufs[VM_MAX_BUFS];
@@ -242,7 +262,7 @@ int grid_for(const DevProgram& pr, size_t n_items) {
   } while (0)
 
 int launch_named(const char* name, size_t n, const VmBuf* bufs, int n_bufs, int grid_override = 0) {
-  const DevProgram* pr = find_program(name);
+  const DevProgram* pr = find_program(name, n);
   if (!pr) return B200BLS_E_PROGRAM;
   return launch_program(*pr, n, bufs, n_bufs, grid_override);
 }
@@ -264,7 +284,7 @@ int sum_dev(bool g2, const void* pts, void* out, size_t n) {
     CU(cudaMemsetAsync(out, 0, w, STREAM));
     return 0;
   }
-  const DevProgram* p1 = find_program(n1);
+  const DevProgram* p1 = find_program(n1, n);
   if (!p1) return B200BLS_E_PROGRAM;
   int grid = grid_for(*p1, n);
   size_t raw_bytes = (size_t)(g2 ? 3 : 2) * 6 * sizeof(uint4) * grid;
@@ -287,7 +307,7 @@ int miller_product_dev(const void* P, const void* Q, void* out576, size_t n) {
   VmBuf ba[3] = {vb(P, 96), vb(Q, 192), vb(cur().scratch[1].ptr, (long long)n)};
   rc = launch_named("miller_raw", n, ba, 3);
   if (rc) return rc;
-  const DevProgram* p1 = find_program("f12_prod1");
+  const DevProgram* p1 = find_program("f12_prod1", n);
   if (!p1) return B200BLS_E_PROGRAM;
   int grid = grid_for(*p1, n);
   rc = ensure_scratch(2, (size_t)576 * grid);
@@ -461,7 +481,7 @@ int b200bls_init(int device) {
     c.programs[nm] = dp;
   }
   const char* env = getenv("B200BLS_CTAS_PER_SM");
-  if (env && env[0] >= '1' && env[0] <= '3') c.ctas_per_sm = env[0] - '0';
+  if (env && env[0] >= '0' && env[0] <= '3') c.ctas_per_sm = env[0] - '0';
   c.device = device;
   c.ready = true;
   return 0;
@@ -505,7 +525,7 @@ int b200bls_sm_count(void) { return g_ctx.ready ? g_ctx.sm_count : 0; }
 
 int b200bls_set_ctas_per_sm(int n) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (n < 1 || n > 3) return fail(B200BLS_E_ARG, "ctas_per_sm must be 1, 2 or 3");
+  if (n < 0 || n > 3) return fail(B200BLS_E_ARG, "ctas_per_sm must be 0 (auto), 1, 2 or 3");
   g_ctx.ctas_per_sm = n;
   return 0;
 }

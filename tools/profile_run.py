@@ -11,6 +11,8 @@ sys.path.insert(0, os.path.join(ROOT, "python-bls_b200"))
 from bls_b200 import _lib, engine                           # noqa: E402
 
 _lib.init(0)
+if _lib.lib.b200bls_get_ctas_per_sm() == 0:
+    _lib.check(_lib.lib.b200bls_set_ctas_per_sm(3))
 n = _lib.lib.b200bls_sm_count() * 128 * _lib.lib.b200bls_get_ctas_per_sm()
 rng = np.random.default_rng(7)
 P = rng.integers(0, 256, size=(n, 96), dtype=np.uint8)
