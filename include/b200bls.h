@@ -49,6 +49,12 @@ void b200bls_shutdown(void);
 const char* b200bls_last_error(void);
 int b200bls_sm_count(void);              /* SMs of the initialised device, 0 if none */
 int b200bls_sync(void);                  /* wait for the library stream */
+/* The library owns 4 CUDA streams.  *_dev and *_async entry points enqueue on the stream
+ * selected here (default 0); launches on different streams overlap, which removes the tail-wave
+ * loss between back-to-back batches.  b200bls_sync() waits for all of them; the timer brackets
+ * all of them.  Synchronous host-buffer entry points run on the selected stream. */
+int b200bls_set_stream(int idx);
+int b200bls_stream_count(void);
 /* Launch shape = CTAs of 128 threads per SM: 1 (18 shared + 21 Tensor-Memory Fq2 workspace slots
  * per thread), 2 (9 + 10) or 3 (6 + 5).  More CTAs per SM = more throughput, but a longer single
  * pass.  0 (default, or environment variable B200BLS_CTAS_PER_SM) chooses per call the shape
