@@ -47,10 +47,8 @@ constexpr uint32_t Q_INV_NEG = 0xfffcfffdu;  // -q^-1 mod 2^32
 #ifdef B200BLS_HOSTSIM
 static const uint32_t kQ[NL] = B200BLS_Q_LIMBS;
 static const uint32_t kQ2[NL] = B200BLS_2Q_LIMBS;
-static const uint32_t kQQ4[2 * NL] = B200BLS_4QQ_LIMBS;
 #define QL(i) kQ[i]
 #define Q2L(i) kQ2[i]
-#define QQ4L(i) kQQ4[i]
 #else
 // Compile-time immediates: the modulus limbs become instruction immediates / constant
 // bank operands instead of live registers.
@@ -62,13 +60,8 @@ __device__ __forceinline__ constexpr uint32_t q2_limb(int i) {
   constexpr uint32_t t[NL] = B200BLS_2Q_LIMBS;
   return t[i];
 }
-__device__ __forceinline__ constexpr uint32_t qq4_limb(int i) {
-  constexpr uint32_t t[2 * NL] = B200BLS_4QQ_LIMBS;
-  return t[i];
-}
 #define QL(i) q_limb(i)
 #define Q2L(i) q2_limb(i)
-#define QQ4L(i) qq4_limb(i)
 #endif
 
 // ---------------------------------------------------------------------------------------

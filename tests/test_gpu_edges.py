@@ -1,0 +1,80 @@
+"""GPU: edge cases of the batched C ABI -- empty batches, ragged sizes around CTA / wave
+boundaries, scalars 0 / n / > n, infinity operands, every launch shape."""
+import numpy as np
+import pytest
+
+import bls_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def ser1(p):
+    return p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+
+
+def ser2(p):
+    return b"".join(c.to_bytes(48, "big") for c in (p[0][0], p[0][1], p[1][0], p[1][1]))
+
+
+def test_empty_batches():
+    from bls_b200 import engine
+    assert engine.pairing_batch(b"", b"").size == 0
+    assert engine.hash_to_g2(b"").size == 0
+    assert engine.verify_batch(b"", b"", b"").size == 0
+    assert engine.scalar_mul(b"", b"", True).size == 0
+    out, ok = engine.decompress(b"", False)
+    assert out.size == 0 and ok.size == 0
+
+
+def test_scalar_edge_values():
+    """k = 0, 1, n - 1, n, n + 5, 2^256 - 1 on both groups vs the oracle"""
+    from bls_b200 import engine
+    ks = [0, 1, O.N - 1, O.N, O.N + 5, (1 << 256) - 1]
+    sc = b"".join(k.to_bytes(32, "big") for k in ks)
+    for g2, G, ser in ((False, O.G1, ser1), (True, O.G2, ser2)):
+        w = 192 if g2 else 96
+        out = engine.scalar_mul(ser(G) * len(ks), sc, g2).tobytes()
+        for i, k in enumerate(ks):
+            want = O.to_aff(O.jac_mul(k % O.N, O.to_jac(G)))
+            want_b = bytes(w) if want[2] else ser(want)
+            assert out[w * i:w * (i + 1)] == want_b, (g2, k)
+    # infinity times anything is infinity
+    assert engine.scalar_mul(bytes(96), (5).to_bytes(32, "big"), False).tobytes() == bytes(96)
+
+
+@pytest.mark.parametrize("ctas", [1, 2, 3])
+def test_ragged_batches_every_shape(ctas):
+    """batch sizes around the CTA (128) and wave boundaries, one known pairing repeated"""
+    from bls_b200 import _lib, engine
+    _lib.init()
+    _lib.check(_lib.lib.b200bls_set_ctas_per_sm(ctas))
+    try:
+        p, q = O.aff_mul(9, O.G1), O.aff_mul(4, O.G2)
+        want = O.f12_serialize(O.ate_pairing(p, q))
+        wave = _lib.lib.b200bls_sm_count() * 128 * ctas
+        for n in (1, 127, 129, wave - 1, wave + 1):
+            out = engine.pairing_batch(ser1(p) * n, ser2(q) * n).tobytes()
+            assert out[:576] == want and out[-576:] == want
+            assert out == want * n
+    finally:
+        _lib.check(_lib.lib.b200bls_set_ctas_per_sm(0))
+
+
+def test_streams_overlap_and_stay_independent():
+    """the same batch enqueued on all four library streams gives four identical results"""
+    from bls_b200 import _lib, engine
+    from bls_b200._lib import check, lib
+    _lib.init()
+    n = 1000
+    p, q = O.aff_mul(2, O.G1), O.aff_mul(3, O.G2)
+    dP = engine.DeviceBuffer(96 * n).upload(ser1(p) * n)
+    dQ = engine.DeviceBuffer(192 * n).upload(ser2(q) * n)
+    outs = [engine.DeviceBuffer(576 * n) for _ in range(lib.b200bls_stream_count())]
+    for k, o in enumerate(outs):
+        check(lib.b200bls_set_stream(k))
+        check(lib.b200bls_pairing_batch_dev(dP.ptr, dQ.ptr, o.ptr, n))
+    check(lib.b200bls_set_stream(0))
+    check(lib.b200bls_sync())
+    want = O.f12_serialize(O.ate_pairing(p, q)) * n
+    for o in outs:
+        assert o.download().tobytes() == want
