@@ -271,9 +271,14 @@ def build_miller_raw():
 
 
 def _f12_tree_product(prog, f, nt=128):
+    from .curve import _copy2
     off = nt // 2
+    first = True
     while off >= 1:
         cs = f.coeffs()
+        if first:
+            cs = [_copy2(prog, c) for c in cs]              # never XMOV a fixed-cell variable
+            first = False
         prog.sync()
         other = [prog.xmov2(c, off) for c in cs]
         prog.sync()

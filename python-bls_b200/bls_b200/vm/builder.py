@@ -372,11 +372,9 @@ class Program:
     # ---- assembly ---------------------------------------------------------------------------
     def assemble(self, n_slots, n_cold=1024, n_tmem=0):
         """n_slots Fq2 slots in shared memory plus n_tmem slots in Tensor Memory (slot indices
-        n_slots .. n_slots + n_tmem - 1).  TMEM lanes are private to their thread, so programs
-        with cross-thread reads (XMOV2) must be assembled with n_tmem = 0."""
-        if n_tmem and any(op.name == "XMOV2" for op in self.ops):
-            raise RuntimeError("cross-thread reads need a shared-memory-only workspace")
-        asm = _assemble(self, n_slots + n_tmem, n_cold)
+        n_slots .. n_slots + n_tmem - 1).  TMEM lanes are private to their thread, so the operands of
+        cross-thread reads (XMOV2) are kept in / moved to shared-memory slots."""
+        asm = _assemble(self, n_slots + n_tmem, n_cold, n_smem=n_slots)
         asm.n_slots, asm.n_tmem = n_slots, n_tmem
         return asm
 
@@ -404,7 +402,9 @@ class Assembled:
         return out
 
 
-def _assemble(prog, n_slots, n_cold):
+def _assemble(prog, n_slots, n_cold, n_smem=None):
+    if n_smem is None:
+        n_smem = n_slots
     ops = prog.ops
     n = len(ops)
     INF = 1 << 60
@@ -449,17 +449,21 @@ def _assemble(prog, n_slots, n_cold):
     def emit(name, d=0, a=0, b=0, aux=0):
         out.append((isa.OPCODE[name] | (aux << 8), d, a, b))
 
-    def alloc_slot(i, pinned):
-        if not free_slots and skip_stack:
+    def alloc_slot(i, pinned, smem_only=False):
+        cands = [x for x in free_slots if x < n_smem] if smem_only else free_slots
+        if not cands and skip_stack:
             raise RuntimeError("spill needed inside a skip region (op %d)" % i)
-        if free_slots:
-            s = free_slots.pop()
+        if cands:
+            s = min(cands) if smem_only else free_slots[-1]
+            free_slots.remove(s)
             stats["max_slots"] = max(stats["max_slots"], n_slots - len(free_slots))
             return s
         # evict the resident value with the farthest next use
         best, best_use = None, -1
         for vid in slot_of:
             if vid in pinned or vid in fixed or vid in region_pins:
+                continue
+            if smem_only and slot_of[vid] >= n_smem:
                 continue
             nu = next_use(vid, i - 1)
             if nu > best_use:
@@ -552,15 +556,24 @@ def _assemble(prog, n_slots, n_cold):
         partial_def = d_is_data and isinstance(op.d, Half)
         if partial_def and root(op.d).id in slot_of:
             pinned.add(root(op.d).id)
+        xmov = op.name == "XMOV2"
         # make sources resident
         for x in srcs:
             vid = root(x).id
+            if xmov and vid in slot_of and slot_of[vid] >= n_smem:
+                # another thread reads this value: it must sit in shared memory
+                if vid in fixed:
+                    raise RuntimeError("XMOV2 of a fixed-cell value that lives in tensor memory")
+                s2 = alloc_slot(i, pinned, smem_only=True)
+                emit("MOV2", 2 * s2, 2 * slot_of[vid])
+                free_slots.append(slot_of[vid])
+                slot_of[vid] = s2
             if vid not in slot_of:
                 if vid not in cold_of:
                     raise RuntimeError("use of undefined value at op %d (%s)" % (i, op.name))
                 if skip_stack:
                     raise RuntimeError("fill needed inside a skip region (op %d)" % i)
-                s = alloc_slot(i, pinned)
+                s = alloc_slot(i, pinned, smem_only=xmov)
                 slot_of[vid] = s
                 emit("FILL2", 2 * s, cold_of[vid])
                 stats["fills"] += 1
@@ -610,7 +623,7 @@ def _assemble(prog, n_slots, n_cold):
                         emit("FILL2", 2 * s, cold_of[r.id])
                         stats["fills"] += 1
                     else:
-                        slot_of[r.id] = alloc_slot(i, pinned)
+                        slot_of[r.id] = alloc_slot(i, pinned, smem_only=xmov)
                 if r.id in cold_of:              # cold copy goes stale on a (partial) write
                     free_cold.append(cold_of.pop(r.id))
                 conc[0] = 2 * slot_of[r.id] + (op.d.half if isinstance(op.d, Half) else 0)

@@ -91,10 +91,11 @@ def test_sum_programs_with_skipped_and_executed_regions(g2):
     plist = pts + [pts[1], pts[1], O.aff_neg(pts[2])]
     data = b"".join(ser(p) for p in plist) + bytes(w)
     n = len(data) // w
-    a1 = curve.build_sum_pass1(g2)().assemble(18)
-    a2 = curve.build_sum_pass2(g2)().assemble(18)
     want = ser((O.g2_sum if g2 else O.g1_sum)(plist))
-    for honor in (True, False):
+    for honor, (ns, ntm) in ((True, (18, 0)), (False, (18, 0)), (True, (9, 10))):
+        # (9, 10): cross-thread reads with part of the workspace in (thread-private) tensor memory
+        a1 = curve.build_sum_pass1(g2)().assemble(ns, n_tmem=ntm)
+        a2 = curve.build_sum_pass2(g2)().assemble(ns, n_tmem=ntm)
         nb = 2
         raw = np.zeros((3 if g2 else 2) * 6 * nb * 16, dtype=np.uint8)
         hostsim.run(a1, {0: np.frombuffer(data, dtype=np.uint8).copy(), 1: raw}, {0: w, 1: nb}, n,
