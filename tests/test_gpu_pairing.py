@@ -76,3 +76,32 @@ def test_bilinearity_property():
     out = engine.pairing_batch(b"".join(map(pb, ps)), b"".join(map(qb, qs))).tobytes()
     assert out[:576] == out[576:1152] == out[1152:]
     assert out[:576] != O.f12_serialize(O.F12_ONE)
+
+
+def test_config2_full_size_checksum_of_checksums():
+    """BASELINE config 2 at full size (65,536 pairs): the product of all per-pair outputs of
+    pairing_batch, the single-final-exponentiation pairing_multi of the same pairs, and the
+    oracle's e((sum a_i b_i) G1, G2) must be the same 576 bytes."""
+    from bls_b200 import engine, synth
+    n = 65536
+    a = synth.scalars(synth.SEED_PAIRING, n)
+    b = synth.scalars(synth.SEED_PAIRING + 1, n)
+    g1 = np.frombuffer(O.G1[0].to_bytes(48, "big") + O.G1[1].to_bytes(48, "big"), dtype=np.uint8)
+    g2 = np.frombuffer(b"".join(c.to_bytes(48, "big") for c in (O.G2[0] + O.G2[1])), dtype=np.uint8)
+    P = engine.scalar_mul(np.tile(g1, n), a, False)
+    Q = engine.scalar_mul(np.tile(g2, n), b, True)
+    e = engine.pairing_batch(P, Q)
+    # 16-level product tree over the GT elements (batched Fq12 multiplications on the GPU)
+    level = e.reshape(n, 576)
+    while level.shape[0] > 1:
+        half = level.shape[0] // 2
+        level = engine.field_op(12, "mul", level[:half].copy(), level[half:].copy()).reshape(half, 576)
+    prod = level.tobytes()
+    assert engine.pairing_multi(P, Q).tobytes() == prod
+    s = sum(int.from_bytes(bytes(x), "big") * int.from_bytes(bytes(y), "big") for x, y in zip(a, b)) % O.N
+    assert prod == O.f12_serialize(O.ate_pairing(O.aff_mul(s, O.G1), O.G2))
+    # and two individual outputs against the oracle
+    for i in (0, n - 1):
+        p = O.aff_mul(int.from_bytes(bytes(a[i]), "big"), O.G1)
+        q = O.aff_mul(int.from_bytes(bytes(b[i]), "big"), O.G2)
+        assert e[576 * i:576 * (i + 1)].tobytes() == O.f12_serialize(O.ate_pairing(p, q))
