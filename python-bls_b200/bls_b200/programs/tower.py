@@ -157,16 +157,16 @@ class F12:
 
         z0, z4, z3 = self.c0.a0, self.c0.a1, self.c0.a2
         z2, z1, z5 = self.c1.a0, self.c1.a1, self.c1.a2
+        prog = z0.prog
         t0, t1 = fp4_sqr(z0, z1)
-        r0 = (t0 - z0).dbl() + t0
-        r1 = (t1 + z1).dbl() + t1
+        r0 = prog.tri2(t0, z0, False)          # 3 t0 - 2 z0
+        r1 = prog.tri2(t1, z1, True)           # 3 t1 + 2 z1
         t0, t1 = fp4_sqr(z2, z3)
         t2, t3 = fp4_sqr(z4, z5)
-        r4 = (t0 - z4).dbl() + t0
-        r5 = (t1 + z5).dbl() + t1
-        t0 = t3.mul_xi()
-        r2 = (t0 + z2).dbl() + t0
-        r3 = (t2 - z3).dbl() + t2
+        r4 = prog.tri2(t0, z4, False)
+        r5 = prog.tri2(t1, z5, True)
+        r2 = prog.tri2(t3.mul_xi(), z2, True)
+        r3 = prog.tri2(t2, z3, False)
         return F12(F6(r0, r4, r3), F6(r2, r1, r5))
 
     def mul_by_014(self, l0, l1, l4):

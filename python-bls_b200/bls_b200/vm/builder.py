@@ -341,6 +341,12 @@ class Program:
         assert var.id in self.persistent
         self.emit("MOV2", var, value)
 
+    def tri2(self, a, b, plus):
+        """3a + 2b (plus) or 3a - 2b in one instruction"""
+        r = V2(self)
+        self.emit("TRI2", r, a, b, aux=int(bool(plus)))
+        return r
+
     def update_sel(self, var, f, a):
         """var = f ? a : var, in place (var keeps its cells)"""
         self.emit("CSEL2" if var.width == 2 else "CSEL1", var, a, var, aux=f)

@@ -56,6 +56,8 @@ OPS = [
     ("XMOV2", "c2 c2 i", "d = cell a of thread (tid + b) mod block size"),
     ("SKIPZ", "f i -", "if no thread of the warp has flag[d]: skip the next a instructions"),
     ("FLDB", "f u i", "flag[d] = (byte b of the item's record in buffer a) != 0"),
+    # fused: one decode / load / store round instead of three
+    ("TRI2", "c2 c2 c2", "d = 3a - 2b (aux = 0) or 3a + 2b (aux = 1)"),
 ]
 
 OPCODE = {name: i for i, (name, _, _) in enumerate(OPS)}

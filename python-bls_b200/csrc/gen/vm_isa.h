@@ -48,9 +48,10 @@ enum VmOp : int {
   OP_XMOV2 = 44,  // c2 c2 i  d = cell a of thread (tid + b) mod block size
   OP_SKIPZ = 45,  // f i -  if no thread of the warp has flag[d]: skip the next a instructions
   OP_FLDB = 46,  // f u i  flag[d] = (byte b of the item's record in buffer a) != 0
-  OP__COUNT = 47
+  OP_TRI2 = 47,  // c2 c2 c2  d = 3a - 2b (aux = 0) or 3a + 2b (aux = 1)
+  OP__COUNT = 48
 };
 // operand handling per opcode: bit0/1 load a as Fq/Fq2, bit2/3 load b as Fq/Fq2,
 // bit4/5 store the result to d as Fq/Fq2
 enum VmOpInfo : unsigned { VM_A1 = 1, VM_A2 = 2, VM_B1 = 4, VM_B2 = 8, VM_D1 = 16, VM_D2 = 32 };
-#define VM_OP_INFO_TABLE {0, 42, 34, 42, 42, 34, 34, 34, 34, 34, 38, 21, 17, 21, 21, 17, 17, 17, 16, 32, 1, 2, 1, 5, 10, 0, 0, 0, 0, 0, 0, 0, 42, 21, 16, 16, 1, 0, 32, 2, 2, 2, 32, 0, 32, 0, 0}
+#define VM_OP_INFO_TABLE {0, 42, 34, 42, 42, 34, 34, 34, 34, 34, 38, 21, 17, 21, 21, 17, 17, 17, 16, 32, 1, 2, 1, 5, 10, 0, 0, 0, 0, 0, 0, 0, 42, 21, 16, 16, 1, 0, 32, 2, 2, 2, 32, 0, 32, 0, 0, 42}

@@ -73,6 +73,9 @@ def run(prog, bufs, n_items, n_threads=1, strides=None, out_bufs=None):
                     r = list(a)
                 elif nm == "MULFP2":
                     r = [a[0] * b % Q, a[1] * b % Q]
+                elif nm == "TRI2":
+                    sg = 1 if op.aux else -1
+                    r = [(3 * a[0] + sg * 2 * b[0]) % Q, (3 * a[1] + sg * 2 * b[1]) % Q]
                 elif nm == "MUL1":
                     r = a * b % Q
                 elif nm == "SQR1":
