@@ -233,11 +233,9 @@ def _tree_reduce(prog, c, acc, nt=128):
     while off >= 1:
         packed = _pack_point(prog, c, acc)
         if first and c.g2:
-            packed = [_copy2(prog, v) for v in packed]      # never XMOV a fixed-cell variable
-            first = False
-        prog.sync()
-        other = [prog.xmov2(v, off) for v in packed]
-        prog.sync()
+            packed = [_copy2(prog, v) for v in packed]      # never exchange a fixed-cell variable
+        first = False
+        other = prog.exchange(packed, off)
         acc = c.add(acc, _unpack_point(prog, c, other))
         off //= 2
     return acc

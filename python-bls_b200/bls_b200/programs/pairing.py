@@ -277,12 +277,9 @@ def _f12_tree_product(prog, f, nt=128):
     while off >= 1:
         cs = f.coeffs()
         if first:
-            cs = [_copy2(prog, c) for c in cs]              # never XMOV a fixed-cell variable
+            cs = [_copy2(prog, c) for c in cs]              # never exchange a fixed-cell variable
             first = False
-        prog.sync()
-        other = [prog.xmov2(c, off) for c in cs]
-        prog.sync()
-        f = f * F12.from_coeffs(other)
+        f = f * F12.from_coeffs(prog.exchange(cs, off))
         off //= 2
     return f
 

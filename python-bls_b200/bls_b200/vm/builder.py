@@ -370,10 +370,15 @@ class Program:
     def sync(self):
         self.emit("SYNC")
 
-    def xmov2(self, v, lane_off):
-        r = V2(self)
-        self.emit("XMOV2", r, v, lane_off)
-        return r
+    def exchange(self, values, lane_off):
+        """cross-thread read: returns, for every thread, the values held by thread
+        (tid + lane_off) mod CTA size.  Assembled as ONE unit: every source is first made
+        resident in shared memory and every destination cell is reserved (all spills, fills and
+        relocations happen here), THEN barrier, the XMOV2 reads, barrier.  No memory traffic of
+        any thread can fall between a barrier and the reads that depend on it."""
+        outs = [V2(self) for _ in values]
+        self.emit("XCHG", outs, list(values), int(lane_off))
+        return outs
 
     # ---- assembly ---------------------------------------------------------------------------
     def assemble(self, n_slots, n_cold=1024, n_tmem=0):
@@ -421,7 +426,8 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
     # use positions per value
     uses = {}
     for i, op in enumerate(ops):
-        for x in (op.d, op.a, op.b, op.aux):
+        operands = (list(op.d) + list(op.a)) if op.name == "XCHG" else (op.d, op.a, op.b, op.aux)
+        for x in operands:
             if _is_val(x):
                 uses.setdefault(root(x).id, []).append(i)
     for v in prog.keep:
@@ -504,6 +510,40 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
             marks[0] = len(out)
         if i == prog.section_marks["epilogue"]:
             marks[1] = len(out)
+        if op.name == "XCHG":
+            if skip_stack:
+                raise RuntimeError("exchange inside a skip region")
+            srcs_x, dsts_x = list(op.a), list(op.d)
+            hold = set(v.id for v in srcs_x)
+            for v in srcs_x:
+                if v.id in slot_of and slot_of[v.id] >= n_smem:
+                    if v.id in fixed:
+                        raise RuntimeError("exchange of a fixed-cell value that lives in tensor memory")
+                    s2 = alloc_slot(i, hold, smem_only=True)
+                    emit("MOV2", 2 * s2, 2 * slot_of[v.id])
+                    free_slots.append(slot_of[v.id])
+                    slot_of[v.id] = s2
+                elif v.id not in slot_of:
+                    if v.id not in cold_of:
+                        raise RuntimeError("use of undefined value at op %d (XCHG)" % i)
+                    s2 = alloc_slot(i, hold, smem_only=True)
+                    slot_of[v.id] = s2
+                    emit("FILL2", 2 * s2, cold_of[v.id])
+                    stats["fills"] += 1
+            for dv in dsts_x:
+                slot_of[dv.id] = alloc_slot(i, hold, smem_only=True)
+                hold.add(dv.id)
+            emit("SYNC")
+            for dv, v in zip(dsts_x, srcs_x):
+                emit("XMOV2", 2 * slot_of[dv.id], 2 * slot_of[v.id], int(op.b))
+            emit("SYNC")
+            for v in srcs_x:
+                if v.id not in fixed and next_use(v.id, i) == INF:
+                    release(v.id)
+            for dv in dsts_x:
+                if next_use(dv.id, i) == INF:
+                    release(dv.id)
+            continue
         if op.name == "SKIP_END":
             at = skip_stack.pop()
             w0, d, _, b = out[at]
@@ -562,24 +602,17 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
         partial_def = d_is_data and isinstance(op.d, Half)
         if partial_def and root(op.d).id in slot_of:
             pinned.add(root(op.d).id)
-        xmov = op.name == "XMOV2"
+        if op.name == "XMOV2":
+            raise RuntimeError("XMOV2 is emitted by Program.exchange() only")
         # make sources resident
         for x in srcs:
             vid = root(x).id
-            if xmov and vid in slot_of and slot_of[vid] >= n_smem:
-                # another thread reads this value: it must sit in shared memory
-                if vid in fixed:
-                    raise RuntimeError("XMOV2 of a fixed-cell value that lives in tensor memory")
-                s2 = alloc_slot(i, pinned, smem_only=True)
-                emit("MOV2", 2 * s2, 2 * slot_of[vid])
-                free_slots.append(slot_of[vid])
-                slot_of[vid] = s2
             if vid not in slot_of:
                 if vid not in cold_of:
                     raise RuntimeError("use of undefined value at op %d (%s)" % (i, op.name))
                 if skip_stack:
                     raise RuntimeError("fill needed inside a skip region (op %d)" % i)
-                s = alloc_slot(i, pinned, smem_only=xmov)
+                s = alloc_slot(i, pinned)
                 slot_of[vid] = s
                 emit("FILL2", 2 * s, cold_of[vid])
                 stats["fills"] += 1
@@ -606,7 +639,7 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
             vid = root(x).id
             if vid not in dying and vid not in fixed and next_use(vid, i) == INF:
                 dying.append(vid)
-        if op.name != "XMOV2":
+        if True:
             for vid in dying:
                 if vid in flag_of:
                     pass
@@ -629,7 +662,7 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                         emit("FILL2", 2 * s, cold_of[r.id])
                         stats["fills"] += 1
                     else:
-                        slot_of[r.id] = alloc_slot(i, pinned, smem_only=xmov)
+                        slot_of[r.id] = alloc_slot(i, pinned)
                 if r.id in cold_of:              # cold copy goes stale on a (partial) write
                     free_cold.append(cold_of.pop(r.id))
                 conc[0] = 2 * slot_of[r.id] + (op.d.half if isinstance(op.d, Half) else 0)
@@ -638,9 +671,6 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
         if op.name == "SKIPZ":
             skip_stack.append(len(out))
         emit(op.name, conc[0], conc[1], conc[2], aux)
-        if op.name == "XMOV2":
-            for vid in dying:
-                release(vid)
         for vid in dying:
             if vid in flag_of:
                 free_flags.append(flag_of.pop(vid))

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../python-bls_b200/csrc/vm_exec.cuh"
@@ -21,6 +22,10 @@ struct Shared {
   int n_cells;
   int smem_cells;                // cells >= smem_cells model Tensor Memory (thread-private)
   std::vector<uint32_t>* smem;   // per block: [cell][chunk][tid][4]
+  // cross-thread hazard detector (all threads of a block step together, so one flag per cell):
+  // a cell written since the last barrier must not be read by another thread, and a cell read
+  // by another thread must not be written before the next barrier
+  std::vector<unsigned char> written, xread;
   std::vector<uint32_t> cold;    // [(g*6+k)*total + gtid][4]
 };
 
@@ -37,12 +42,18 @@ struct HostEnv {
     for (int k = 0; k < 3; k++) memcpy(&x.v[4 * k], cellp(c, k, tid), 16);
   }
   void st1(int c, const fp& x) {
+    if (c < sh->smem_cells) {
+      if (sh->xread[c]) abort();   // write-after-cross-read without a barrier
+      sh->written[c] = 1;
+    }
     for (int k = 0; k < 3; k++) memcpy(cellp(c, k, tid), &x.v[4 * k], 16);
   }
   void ld2(int c, fp2& x) { ld1(c, x.c0); ld1(c + 1, x.c1); }
   void st2(int c, const fp2& x) { st1(c, x.c0); st1(c + 1, x.c1); }
   void ld2_lane(int c, int off, fp2& x) {
     if (c + 1 >= sh->smem_cells) abort();  // TMEM lanes cannot be read by another thread
+    if (sh->written[c] || sh->written[c + 1]) abort();  // cross-read of a cell written after the last barrier
+    sh->xread[c] = sh->xread[c + 1] = 1;
     int t = (tid + off) % sh->nt;
     for (int k = 0; k < 3; k++) {
       memcpy(&x.c0.v[4 * k], cellp(c, k, t), 16);
@@ -121,7 +132,10 @@ struct HostEnv {
       memcpy(&x.c1.v[4 * k], coldp(g, 3 + k), 16);
     }
   }
-  void sync() {}
+  void sync() {
+    std::fill(sh->written.begin(), sh->written.end(), 0);
+    std::fill(sh->xread.begin(), sh->xread.end(), 0);
+  }
 };
 }  // namespace
 
@@ -138,6 +152,8 @@ extern "C" int hs_vm_run(const uint32_t* code, int n_ins, int body_start, int ep
   sh.total = nt * n_blocks;
   sh.n_cells = 2 * (n_slots + n_tmem);
   sh.smem_cells = 2 * n_slots;
+  sh.written.assign(sh.n_cells, 0);
+  sh.xread.assign(sh.n_cells, 0);
   std::vector<std::vector<uint32_t>> smem(n_blocks);
   for (auto& s : smem) s.assign((size_t)sh.n_cells * 3 * nt * 4, 0xdeadbeefu);
   sh.smem = smem.data();

@@ -122,3 +122,18 @@ def test_decompress_public_keys():
         except ValueError:
             assert ok[i] == 0, i
     assert 0 < int(ok.sum()) < len(pks)
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_sums_are_deterministic_under_repetition(g2):
+    """the reduction exchanges data between threads: 40 repetitions at a size that spans many
+    CTAs and several item blocks per CTA must give the same (correct) point every time"""
+    from bls_b200 import engine, synth
+    n = 125000
+    sc = synth.scalars(77, n)
+    G = O.G2 if g2 else O.G1
+    ser = ser2 if g2 else ser1
+    pts = engine.scalar_mul(np.tile(np.frombuffer(ser(G), dtype=np.uint8), n), sc, g2)
+    want = ser(O.aff_mul(sum(int.from_bytes(bytes(r), "big") for r in sc) % N, G))
+    for rep in range(40):
+        assert engine.point_sum(pts, g2).tobytes() == want, rep

@@ -41,10 +41,11 @@ def run(prog, bufs, n_items, n_threads=1, strides=None, out_bufs=None):
             nm = op.name
             if nm in ("SYNC", "SKIPZ", "SKIP_END"):
                 continue
-            if nm == "XMOV2":
-                vals = [list(get(state[(t + op.b) % n_threads], op.a)) for t in range(n_threads)]
-                for t in range(n_threads):
-                    put(state[t], op.d, vals[t])
+            if nm == "XCHG":
+                for dv, sv in zip(op.d, op.a):
+                    vals = [list(get(state[(t + op.b) % n_threads], sv)) for t in range(n_threads)]
+                    for t in range(n_threads):
+                        put(state[t], dv, vals[t])
                 continue
             for t in range(n_threads):
                 st = state[t]
