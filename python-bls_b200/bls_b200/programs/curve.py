@@ -219,23 +219,11 @@ def _unpack_point(prog, c, vals):
     return (vals[0].c0, vals[0].c1, vals[1].c0)
 
 
-def _copy2(prog, v):
-    from ..vm.builder import V2
-    r = V2(prog)
-    prog.emit("MOV2", r, v)
-    return r
-
-
 def _tree_reduce(prog, c, acc, nt=128):
     """sum of every thread's acc into thread 0 (all threads execute the same adds)"""
     off = nt // 2
-    first = True
     while off >= 1:
-        packed = _pack_point(prog, c, acc)
-        if first and c.g2:
-            packed = [_copy2(prog, v) for v in packed]      # never exchange a fixed-cell variable
-        first = False
-        other = prog.exchange(packed, off)
+        other = prog.exchange(_pack_point(prog, c, acc), off)
         acc = c.add(acc, _unpack_point(prog, c, other))
         off //= 2
     return acc

@@ -271,15 +271,9 @@ def build_miller_raw():
 
 
 def _f12_tree_product(prog, f, nt=128):
-    from .curve import _copy2
     off = nt // 2
-    first = True
     while off >= 1:
-        cs = f.coeffs()
-        if first:
-            cs = [_copy2(prog, c) for c in cs]              # never exchange a fixed-cell variable
-            first = False
-        f = f * F12.from_coeffs(prog.exchange(cs, off))
+        f = f * F12.from_coeffs(prog.exchange(f.coeffs(), off))
         off //= 2
     return f
 

@@ -494,8 +494,13 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
             stats["spills"] += 1
         return s
 
+    epi0 = prog.section_marks["epilogue"]
+    cur_op = [0]
+
     def release(vid):
-        if vid in fixed:
+        # fixed-cell values live for the whole body loop; in the epilogue (which runs once,
+        # after the last iteration) they die like any other value
+        if vid in fixed and (epi0 is None or cur_op[0] < epi0):
             return
         if vid in slot_of:
             free_slots.append(slot_of.pop(vid))
@@ -506,6 +511,7 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
     skip_stack = []
     region_pins = set()
     for i, op in enumerate(ops):
+        cur_op[0] = i
         if i == prog.section_marks["body"]:
             marks[0] = len(out)
         if i == prog.section_marks["epilogue"]:
@@ -538,7 +544,7 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                 emit("XMOV2", 2 * slot_of[dv.id], 2 * slot_of[v.id], int(op.b))
             emit("SYNC")
             for v in srcs_x:
-                if v.id not in fixed and next_use(v.id, i) == INF:
+                if next_use(v.id, i) == INF:
                     release(v.id)
             for dv in dsts_x:
                 if next_use(dv.id, i) == INF:
@@ -637,7 +643,7 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
         dying = []
         for x in list(srcs) + [y for y in (op.a, op.b, op.aux) if _is_val(y) and isinstance(root(y), Flag)]:
             vid = root(x).id
-            if vid not in dying and vid not in fixed and next_use(vid, i) == INF:
+            if vid not in dying and next_use(vid, i) == INF and (vid not in fixed or (epi0 is not None and i >= epi0)):
                 dying.append(vid)
         if True:
             for vid in dying:
