@@ -3,6 +3,7 @@ interpreter (tests/hostsim: csrc/fp.cuh + vm_exec.cuh with every PTX instruction
 kernel's cell / cold / Tensor-Memory-slot layouts) and must reproduce the golden vectors.  This
 is what lets formulas, the allocator and the limb arithmetic be validated without a GPU."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -12,6 +13,8 @@ import hostsim
 from conftest import load_golden
 
 from bls_b200.programs import curve, fieldops, hashg2, pairing, registry
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _pq(cases):
@@ -123,3 +126,36 @@ def test_field_programs_on_weakly_reduced_edge_values():
         raw = out.tobytes()
         for i, v in enumerate(vals):
             assert raw[576 * i:576 * (i + 1)] == ser(fn(v, vals[len(vals) - 1 - i])), (op, i)
+
+
+def test_host_simulation_detects_cross_thread_hazards():
+    """Regression guard for a race that once slipped through (a spill/fill between the barrier
+    and the cross-thread read of a tree reduction): the host simulation aborts when a cell
+    written after the last barrier is read by another thread.  Inject exactly that into a
+    correct program and expect the simulator process to die."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import sys
+        import numpy as np
+        sys.path[:0] = %r
+        import hostsim
+        from bls_b200.programs import curve
+        from bls_b200.vm import isa
+        asm = curve.build_sum_pass1(True)().assemble(18)
+        rows = asm.code.tolist()
+        k = next(i for i, r in enumerate(rows) if (r[0] & 0xff) == isa.OPCODE["XMOV2"])
+        if sys.argv[1] == "inject":      # a write to the source cell between barrier and read
+            rows.insert(k, [isa.OPCODE["MOV2"], rows[k][2], rows[k][2], 0])
+            if asm.epilogue_start > k: asm.epilogue_start += 1
+        asm.code = np.array(rows, dtype=np.uint16)
+        pts = np.zeros(192 * 4, dtype=np.uint8)
+        raw = np.zeros(3 * 6 * 1 * 16, dtype=np.uint8)
+        hostsim.run(asm, {0: pts, 1: raw}, {0: 192, 1: 1}, 4, n_blocks=1, nt=128)
+        print("finished")
+    ''') % ([os.path.join(ROOT, d) for d in ('python-bls_b200', 'tests', 'oracle')],)
+    ok = subprocess.run([sys.executable, "-c", code, "clean"], capture_output=True, text=True)
+    assert ok.returncode == 0 and "finished" in ok.stdout, ok.stderr[-500:]
+    bad = subprocess.run([sys.executable, "-c", code, "inject"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "finished" not in bad.stdout
