@@ -9,14 +9,19 @@ buffer numbers or small immediates, depending on the opcode.
 OPS = [
     # name        operand kinds (d, a, b)   -- c2/c1 = Fp2/Fp cell, k = const idx,
     #                                           f = flag, u = buffer, i = immediate
+    # the first nine opcodes after NOP are the hot ones of the pairing programs, in the order the
+    # interpreter's range-compare dispatch expects (vm_exec.cuh static_asserts the numbering)
     ("NOP", "", ""),
-    ("MUL2", "c2 c2 c2", "d = a * b in Fq2"),
-    ("SQR2", "c2 c2 -", "d = a^2"),
     ("ADD2", "c2 c2 c2", ""),
     ("SUB2", "c2 c2 c2", ""),
-    ("NEG2", "c2 c2 -", ""),
-    ("DBL2", "c2 c2 -", "d = 2a"),
+    ("SQR2", "c2 c2 -", "d = a^2"),
+    ("MUL2", "c2 c2 c2", "d = a * b in Fq2"),
     ("MULXI2", "c2 c2 -", "d = a * (1 + u)"),
+    ("TRI2", "c2 c2 c2", "d = 3a - 2b (aux = 0) or 3a + 2b (aux = 1)"),
+    ("FILL2", "c2 g -", "d <- cold[a]"),
+    ("SPILL2", "g c2 -", "cold[d] <- a   (global-memory spill area)"),
+    ("DBL2", "c2 c2 -", "d = 2a"),
+    ("NEG2", "c2 c2 -", ""),
     ("CONJ2", "c2 c2 -", "d = (a.c0, -a.c1)"),
     ("MOV2", "c2 c2 -", ""),
     ("MULFP2", "c2 c2 c1", "d = a * b, b in Fq"),
@@ -50,14 +55,11 @@ OPS = [
     ("LDRAW2", "c2 u i", "d = Montgomery limbs from internal SoA buffer a, element b"),
     ("STRAW2", "u c2 i", "internal SoA buffer d, element b <- a"),
     ("STRAWB2", "u c2 i", "as STRAW2 but only thread 0 of the block, item = block index"),
-    ("SPILL2", "g c2 -", "cold[d] <- a   (global-memory spill area)"),
-    ("FILL2", "c2 g -", "d <- cold[a]"),
     ("SYNC", "- - -", "block barrier"),
     ("XMOV2", "c2 c2 i", "d = cell a of thread (tid + b) mod block size"),
     ("SKIPZ", "f i -", "if no thread of the warp has flag[d]: skip the next a instructions"),
     ("FLDB", "f u i", "flag[d] = (byte b of the item's record in buffer a) != 0"),
     # fused: one decode / load / store round instead of three
-    ("TRI2", "c2 c2 c2", "d = 3a - 2b (aux = 0) or 3a + 2b (aux = 1)"),
 ]
 
 OPCODE = {name: i for i, (name, _, _) in enumerate(OPS)}

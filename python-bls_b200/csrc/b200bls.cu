@@ -471,7 +471,9 @@ int b200bls_init(int device) {
     dp.ctas = (int)en.ctas;
     size_t code_bytes = (size_t)(en.n_ins + 1) * sizeof(uint2);
     size_t const_bytes = (size_t)en.n_consts * 3 * sizeof(uint4);
-    CU(cudaMalloc(&dp.code, code_bytes));
+    // 64 instructions of slack: the interpreter prefetches the instruction stream two L1 lines ahead
+    CU(cudaMalloc(&dp.code, code_bytes + 64 * sizeof(uint2)));
+    CU(cudaMemset(dp.code, 0, code_bytes + 64 * sizeof(uint2)));
     CU(cudaMalloc(&dp.consts, const_bytes));
     CU(cudaMemcpy(dp.code, blob + en.code_off, code_bytes, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dp.consts, blob + en.consts_off, const_bytes, cudaMemcpyHostToDevice));
