@@ -167,7 +167,9 @@ def run_gpu(args, rank, world, dist):
     from bls_b200._lib import check, lib
     local = int(os.environ.get("LOCAL_RANK", "0"))
     _lib.init(local)
-    check(lib.b200bls_set_ctas_per_sm(3))      # throughput shape: batches overlap on two streams
+    # throughput shape: 4 = one 384-thread CTA per SM (6 shared + 7 Tensor-Memory slots per thread);
+    # batches overlap on two streams
+    check(lib.b200bls_set_ctas_per_sm(int(os.environ.get("B200BLS_BENCH_SHAPE", "4"))))
     n = BATCH
     # --- inputs: NSETS rotating buffer sets so the working set (NSETS * 56.6 MB) exceeds the
     # 126 MB L2 between timed iterations
@@ -255,7 +257,7 @@ def run_gpu(args, rank, world, dist):
 
     # --- secondary metric: signatures verified/s (hash-to-G2 + 2 Miller loops + final exp) on one
     # full wave of VALID signatures sig_i = a_i H(m_i) for the public keys pk_i = a_i G1 = P_i
-    nv = lib.b200bls_sm_count() * 128 * lib.b200bls_get_ctas_per_sm()
+    nv = lib.b200bls_sm_count() * 384
     mh = synth.message_hashes(synth.SEED_BATCH_VERIFY + rank, nv)
     d_mh = engine.DeviceBuffer(32 * nv).upload(mh)
     d_pk = engine.DeviceBuffer(96 * nv).upload(hP[:96 * nv])

@@ -56,10 +56,12 @@ int b200bls_sync(void);                  /* wait for the library stream */
 int b200bls_set_stream(int idx);
 int b200bls_stream_count(void);
 /* Launch shape = CTAs of 128 threads per SM: 1 (18 shared + 21 Tensor-Memory Fq2 workspace slots
- * per thread), 2 (9 + 10) or 3 (6 + 5).  More CTAs per SM = more throughput, but a longer single
- * pass.  0 (default, or environment variable B200BLS_CTAS_PER_SM) chooses per call the shape
- * that finishes an isolated batch soonest; pipelines that keep batches in flight on several
- * streams should select 3. */
+ * per thread), 2 (9 + 10) or 3 (6 + 5); 4 = the "wide" shape, ONE CTA of 384 threads per SM that
+ * owns all 512 Tensor-Memory columns (6 + 7 slots per thread; programs without block-level
+ * reductions only, the others fall back to 3).  More warps per SM = more throughput, but a
+ * longer single pass.  0 (default, or environment variable B200BLS_CTAS_PER_SM) chooses per call
+ * the shape that finishes an isolated batch soonest; pipelines that keep batches in flight on
+ * several streams should select 4. */
 int b200bls_set_ctas_per_sm(int n);
 int b200bls_get_ctas_per_sm(void);
 

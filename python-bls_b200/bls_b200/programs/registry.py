@@ -9,7 +9,10 @@ from . import curve, fieldops, hashg2, pairing
 # program cannot use TMEM (cross-thread reads) the shared-memory-only shape is used, and when
 # it does not fit a shape at all the launcher falls back to fewer CTAs per SM.
 N_SLOTS = 18
-SHAPES = {1: (18, 21), 2: (9, 10), 3: (6, 5)}
+SHAPES = {1: (18, 21), 2: (9, 10), 3: (6, 5), 4: (6, 7)}
+# Shape 4 is the "wide" shape: ONE CTA of 384 threads per SM (same 12 warps as shape 3) that owns all
+# 512 TMEM columns, 168 per group of four warps = 7 slots instead of 5.  TMEM programs only.
+WIDE_SHAPES = {4}
 if os.environ.get("B200BLS_SHAPES"):          # experiments: "ctas:smem_slots:tmem_slots,..."
     SHAPES = {int(c): (int(a), int(b)) for c, a, b in
               (item.split(":") for item in os.environ["B200BLS_SHAPES"].split(","))}

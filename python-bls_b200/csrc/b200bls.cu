@@ -57,6 +57,7 @@ struct DevProgram {
   uint2* code = nullptr;
   uint4* consts = nullptr;
   int n_ins = 0, body_start = 0, epi_start = 0, n_slots = 0, n_cold = 0, n_tmem = 0, ctas = 1;
+  int threads = VM_NT;  // shape 4 ("wide"): one CTA of VM_NT_WIDE threads per SM
 };
 
 struct Staging {
@@ -117,12 +118,13 @@ int ensure_buf(Staging& s, size_t bytes) {
 // grid: ctas_per_sm CTAs per SM at most; fewer when the batch is small
 int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int n_bufs, int grid_override = 0) {
   Context& c = g_ctx;
-  long long blocks_needed = (long long)((n_items + VM_NT - 1) / VM_NT);
+  const int nt = pr.threads;
+  long long blocks_needed = (long long)((n_items + nt - 1) / nt);
   long long max_grid = (long long)c.sm_count * pr.ctas;
   int grid = (int)(blocks_needed < max_grid ? blocks_needed : max_grid);
   if (grid < 1) grid = 1;
   if (grid_override > 0) grid = grid_override;
-  long long total = (long long)grid * VM_NT;
+  long long total = (long long)grid * nt;
   StreamCtx& sc = cur();
   size_t cold_need = (size_t)pr.n_cold * 6 * sizeof(uint4) * total;
   if (cold_need > sc.cold_bytes) {
@@ -130,7 +132,7 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
     if (sc.cold) cudaFree(sc.cold);
     sc.cold = nullptr;
     sc.cold_bytes = 0;
-    size_t want = (size_t)pr.n_cold * 6 * sizeof(uint4) * (size_t)max_grid * VM_NT;
+    size_t want = (size_t)pr.n_cold * 6 * sizeof(uint4) * (size_t)max_grid * nt;
     if (want < cold_need) want = cold_need;
     cudaError_t e = cudaMalloc(&sc.cold, want);
     if (e != cudaSuccess) return fail(B200BLS_E_NOMEM, "cold area cudaMalloc(%zu) failed", want);
@@ -147,16 +149,25 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   p.consts = pr.consts;
   p.cold = sc.cold;
   p.n_items = (long long)n_items;
-  p.n_blocks = (long long)((n_items + VM_NT - 1) / VM_NT);
+  p.n_blocks = (long long)((n_items + nt - 1) / nt);
   p.counter = counter;
   p.smem_cells = 2 * pr.n_slots;
-  p.tmem_cols = pr.n_tmem == 0 ? 0 : (pr.n_tmem * 24 <= 128 ? 128 : (pr.n_tmem * 24 <= 256 ? 256 : 512));
   for (int i = 0; i < n_bufs && i < VM_MAX_BUFS; i++) p.bufs[i] = bufs[i];
-  size_t smem = (size_t)pr.n_slots * 2 * 3 * sizeof(uint4) * VM_NT;
-  if (p.tmem_cols)
-    vm_kernel<true, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
-  else
-    vm_kernel<false, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
+  size_t smem = (size_t)pr.n_slots * 2 * 3 * sizeof(uint4) * nt;
+  if (nt == VM_NT_WIDE) {
+    // three groups of four warps share the SM's 512 columns: 168 each (7 Fq2 slots)
+    if (pr.n_tmem * 24 > 168) return fail(B200BLS_E_PROGRAM, "wide shape: %d TMEM slots do not fit 168 columns", pr.n_tmem);
+    p.tmem_cols = 512;
+    p.tmem_group_cols = 168;
+    vm_kernel<true, 1, VM_NT_WIDE><<<grid, VM_NT_WIDE, smem, sc.stream>>>(p);
+  } else {
+    p.tmem_cols = pr.n_tmem == 0 ? 0 : (pr.n_tmem * 24 <= 128 ? 128 : (pr.n_tmem * 24 <= 256 ? 256 : 512));
+    p.tmem_group_cols = 0;
+    if (p.tmem_cols)
+      vm_kernel<true, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
+    else
+      vm_kernel<false, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
+  }
   CU(cudaGetLastError());
   c.launches++;
   return 0;
@@ -189,6 +200,8 @@ const DevProgram* find_program(const char* base, size_t n_items = 0) {
     if (it != g_ctx.programs.end()) return &it->second;
   } else {
     int want = g_ctx.ctas_per_sm > 0 ? g_ctx.ctas_per_sm : auto_ctas(n_items ? n_items : 1);
+    // the wide shape (id 4) holds as many items per SM as three narrow CTAs and is faster where it exists
+    if (g_ctx.ctas_per_sm == 0 && want == 3) want = 4;
     for (int c = want; c >= 1; c--) {
       auto it = g_ctx.programs.find(name + "@" + std::to_string(c));
       if (it != g_ctx.programs.end()) return &it->second;
@@ -250,7 +263,7 @@ int run_dev(const char* name, size_t n, const DevBuf* db, int n_bufs) {
 
 
 int grid_for(const DevProgram& pr, size_t n_items) {
-  long long blocks_needed = (long long)((n_items + VM_NT - 1) / VM_NT);
+  long long blocks_needed = (long long)((n_items + pr.threads - 1) / pr.threads);
   long long max_grid = (long long)g_ctx.sm_count * pr.ctas;
   long long g = blocks_needed < max_grid ? blocks_needed : max_grid;
   return g < 1 ? 1 : (int)g;
@@ -449,6 +462,7 @@ int b200bls_init(int device) {
   CU(cudaEventCreate(&c.ev1));
   CU(cudaFuncSetAttribute(vm_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   CU(cudaFuncSetAttribute(vm_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  CU(cudaFuncSetAttribute(vm_kernel<true, 1, VM_NT_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   // parse the embedded program blob
   const unsigned char* blob = _binary_programs_bin_start;
   size_t blob_len = (size_t)(_binary_programs_bin_end - _binary_programs_bin_start);
@@ -469,6 +483,10 @@ int b200bls_init(int device) {
     dp.n_cold = (int)en.n_cold;
     dp.n_tmem = (int)en.n_tmem;
     dp.ctas = (int)en.ctas;
+    if (dp.ctas == 4) {  // shape id 4 = the wide shape: one CTA of 384 threads per SM
+      dp.ctas = 1;
+      dp.threads = VM_NT_WIDE;
+    }
     size_t code_bytes = (size_t)(en.n_ins + 1) * sizeof(uint2);
     size_t const_bytes = (size_t)en.n_consts * 3 * sizeof(uint4);
     // 64 instructions of slack: the interpreter prefetches the instruction stream two L1 lines ahead
@@ -483,7 +501,7 @@ int b200bls_init(int device) {
     c.programs[nm] = dp;
   }
   const char* env = getenv("B200BLS_CTAS_PER_SM");
-  if (env && env[0] >= '0' && env[0] <= '3') c.ctas_per_sm = env[0] - '0';
+  if (env && env[0] >= '0' && env[0] <= '4') c.ctas_per_sm = env[0] - '0';
   c.device = device;
   c.ready = true;
   return 0;
@@ -527,7 +545,8 @@ int b200bls_sm_count(void) { return g_ctx.ready ? g_ctx.sm_count : 0; }
 
 int b200bls_set_ctas_per_sm(int n) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (n < 0 || n > 3) return fail(B200BLS_E_ARG, "ctas_per_sm must be 0 (auto), 1, 2 or 3");
+  if (n < 0 || n > 4)
+    return fail(B200BLS_E_ARG, "ctas_per_sm must be 0 (auto), 1, 2, 3 or 4 (one wide CTA of 384 threads)");
   g_ctx.ctas_per_sm = n;
   return 0;
 }

@@ -15,7 +15,10 @@
 
 namespace b200bls {
 
-constexpr int VM_NT = 128;      // threads per CTA
+constexpr int VM_NT = 128;      // threads per CTA (default shapes)
+constexpr int VM_NT_WIDE = 384; // "wide" shape: ONE CTA of 12 warps per SM.  Three 128-thread CTAs can only
+                                // allocate 128 TMEM columns each (power-of-two allocations, 512 per SM); one CTA
+                                // owns all 512 and gives each group of four warps 168 columns = 7 Fq2 slots
 constexpr int VM_MAX_BUFS = 8;
 
 struct VmBuf {
@@ -29,10 +32,11 @@ struct VmParams {
   const uint4* consts;     // Montgomery-form constants, 3 x uint4 each
   uint4* cold;             // [n_cold * 6][total threads]
   long long n_items;
-  long long n_blocks;      // ceil(n_items / VM_NT): item blocks handed out dynamically
+  long long n_blocks;      // ceil(n_items / CTA threads): item blocks handed out dynamically
   int* counter;            // zeroed before the launch; next item block to process
   int smem_cells;          // cells [0, smem_cells) live in shared memory, the rest in Tensor Memory
   int tmem_cols;           // TMEM columns to allocate per CTA (0, 128, 256 or 512)
+  int tmem_group_cols;     // columns owned by each group of four warps (CTAs wider than 128 threads)
   VmBuf bufs[VM_MAX_BUFS];
 };
 
@@ -73,7 +77,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <bool USE_TMEM>
+template <bool USE_TMEM, int NT>
 struct DevEnv {
   uint32_t sm;             // shared workspace (shared-space byte address), already offset by threadIdx.x
   uint32_t tm_base;        // TMEM address of column 0 in this warp's lane quadrant
@@ -98,9 +102,9 @@ struct DevEnv {
 #define VM_IN_SMEM(c) (!USE_TMEM || (c) < smem_cells)
   __device__ __forceinline__ void ld1(int c, fp& x) {
     if (VM_IN_SMEM(c)) {
-      const uint32_t q = sm + c * (3 * VM_NT * 16);
+      const uint32_t q = sm + c * (3 * NT * 16);
 #pragma unroll
-      for (int k = 0; k < 3; k++) unpack(x, k, lds128(q + k * (VM_NT * 16)));
+      for (int k = 0; k < 3; k++) unpack(x, k, lds128(q + k * (NT * 16)));
     } else {
       const uint32_t t = tm_base + (uint32_t)(c - smem_cells) * 12;
       tm_wait_st();
@@ -111,9 +115,9 @@ struct DevEnv {
   }
   __device__ __forceinline__ void st1(int c, const fp& x) {
     if (VM_IN_SMEM(c)) {
-      const uint32_t q = sm + c * (3 * VM_NT * 16);
+      const uint32_t q = sm + c * (3 * NT * 16);
 #pragma unroll
-      for (int k = 0; k < 3; k++) sts128(q + k * (VM_NT * 16), pack(x, k));
+      for (int k = 0; k < 3; k++) sts128(q + k * (NT * 16), pack(x, k));
     } else {
       const uint32_t t = tm_base + (uint32_t)(c - smem_cells) * 12;
       tm_st8(t, x.v);
@@ -122,11 +126,11 @@ struct DevEnv {
   }
   __device__ __forceinline__ void ld2(int c, fp2& x) {
     if (VM_IN_SMEM(c)) {
-      const uint32_t q = sm + c * (3 * VM_NT * 16);
+      const uint32_t q = sm + c * (3 * NT * 16);
 #pragma unroll
-      for (int k = 0; k < 3; k++) unpack(x.c0, k, lds128(q + k * (VM_NT * 16)));
+      for (int k = 0; k < 3; k++) unpack(x.c0, k, lds128(q + k * (NT * 16)));
 #pragma unroll
-      for (int k = 0; k < 3; k++) unpack(x.c1, k, lds128(q + (3 + k) * (VM_NT * 16)));
+      for (int k = 0; k < 3; k++) unpack(x.c1, k, lds128(q + (3 + k) * (NT * 16)));
     } else {
       const uint32_t t = tm_base + (uint32_t)(c - smem_cells) * 12;
       tm_wait_st();
@@ -139,11 +143,11 @@ struct DevEnv {
   }
   __device__ __forceinline__ void st2(int c, const fp2& x) {
     if (VM_IN_SMEM(c)) {
-      const uint32_t q = sm + c * (3 * VM_NT * 16);
+      const uint32_t q = sm + c * (3 * NT * 16);
 #pragma unroll
-      for (int k = 0; k < 3; k++) sts128(q + k * (VM_NT * 16), pack(x.c0, k));
+      for (int k = 0; k < 3; k++) sts128(q + k * (NT * 16), pack(x.c0, k));
 #pragma unroll
-      for (int k = 0; k < 3; k++) sts128(q + (3 + k) * (VM_NT * 16), pack(x.c1, k));
+      for (int k = 0; k < 3; k++) sts128(q + (3 + k) * (NT * 16), pack(x.c1, k));
     } else {
       const uint32_t t = tm_base + (uint32_t)(c - smem_cells) * 12;
       tm_st8(t, x.c0.v);
@@ -153,12 +157,12 @@ struct DevEnv {
     }
   }
   __device__ __forceinline__ void ld2_lane(int c, int off, fp2& x) {
-    int t = (threadIdx.x + off) % VM_NT;
-    const uint32_t q = sm + (t - (int)threadIdx.x) * 16 + c * (3 * VM_NT * 16);
+    int t = (threadIdx.x + off) % NT;
+    const uint32_t q = sm + (t - (int)threadIdx.x) * 16 + c * (3 * NT * 16);
 #pragma unroll
-    for (int k = 0; k < 3; k++) unpack(x.c0, k, lds128(q + k * (VM_NT * 16)));
+    for (int k = 0; k < 3; k++) unpack(x.c0, k, lds128(q + k * (NT * 16)));
 #pragma unroll
-    for (int k = 0; k < 3; k++) unpack(x.c1, k, lds128(q + (3 + k) * (VM_NT * 16)));
+    for (int k = 0; k < 3; k++) unpack(x.c1, k, lds128(q + (3 + k) * (NT * 16)));
   }
   __device__ __forceinline__ void ldc(int idx, fp& x) {
     const uint4* q = p->consts + idx * 3;
@@ -276,12 +280,12 @@ __device__ __forceinline__ void vm_run_section(Env& env, const uint2* code, int 
 // executes relinquish_alloc_permit or exits, which serialises co-resident CTAs -- see
 // tools/experiments/tmem_residency_test.cu.  Hence two instantiations, and the TMEM one always
 // allocates and relinquishes first thing.)
-template <bool USE_TMEM, int MIN_CTAS>
-__global__ void __launch_bounds__(VM_NT, MIN_CTAS) vm_kernel(const __grid_constant__ VmParams p) {
+template <bool USE_TMEM, int MIN_CTAS, int NT = VM_NT>
+__global__ void __launch_bounds__(NT, MIN_CTAS) vm_kernel(const __grid_constant__ VmParams p) {
   extern __shared__ uint4 vm_smem[];
   __shared__ uint32_t s_tmem;
   __shared__ int s_blk;
-  DevEnv<USE_TMEM> env;
+  DevEnv<USE_TMEM, NT> env;
   env.smem_cells = p.smem_cells;
   env.tm_base = 0;
   if (USE_TMEM) {
@@ -299,18 +303,20 @@ __global__ void __launch_bounds__(VM_NT, MIN_CTAS) vm_kernel(const __grid_consta
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
-    env.tm_base = s_tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+    // lane quadrant of this warp (warp % 4) in the upper half-word, column base of its group below
+    env.tm_base = s_tmem + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16) +
+                  (uint32_t)(threadIdx.x >> 7) * (uint32_t)p.tmem_group_cols;
   }
   env.sm = (uint32_t)__cvta_generic_to_shared(vm_smem) + threadIdx.x * 16;
   env.p = &p;
-  env.total = (long long)gridDim.x * VM_NT;
-  const long long gtid = (long long)blockIdx.x * VM_NT + threadIdx.x;
+  env.total = (long long)gridDim.x * NT;
+  const long long gtid = (long long)blockIdx.x * NT + threadIdx.x;
   env.cold = p.cold + gtid;
   env.flags = 0;
   const long long last = p.n_items > 0 ? p.n_items - 1 : 0;
   env.item_raw = gtid;
   env.item = gtid < last ? gtid : last;
-  // prologue once; then item blocks of VM_NT items are fetched from a global counter until the
+  // prologue once; then item blocks of NT items are fetched from a global counter until the
   // batch is exhausted (CTAs that find no work left exit early, so the CTAs of the next launch
   // on another stream can move in: no tail-wave quantisation across back-to-back batches);
   // epilogue once.  One copy of the interpreter loop serves all three sections.
@@ -321,6 +327,9 @@ __global__ void __launch_bounds__(VM_NT, MIN_CTAS) vm_kernel(const __grid_consta
       hi = p.body_start;
       phase = 1;
     } else if (phase == 1) {
+      // (tried: item blocks of 128 fetched per group of four warps through named barriers -- worse:
+      // a wide CTA then stays resident until its slowest group is done and the next launch's CTA
+      // cannot move in, 1.36 vs 1.48 M pairings/s)
       __syncthreads();
       if (threadIdx.x == 0) s_blk = atomicAdd(p.counter, 1);
       __syncthreads();
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(VM_NT, MIN_CTAS) vm_kernel(const __grid_consta
       }
       lo = p.body_start;
       hi = p.epi_start;
-      env.item_raw = blk * VM_NT + threadIdx.x;
+      env.item_raw = blk * NT + threadIdx.x;
       env.item = env.item_raw < last ? env.item_raw : last;
     } else {
       lo = p.epi_start;

@@ -21,7 +21,7 @@ Q[:, ::48] &= 0x0f
 dP, dQ, dO = engine.DeviceBuffer(96 * n).upload(P), engine.DeviceBuffer(192 * n).upload(Q), engine.DeviceBuffer(576 * n)
 progs = sys.argv[1:] or ["pairing"]
 for prog in progs:
-    for ctas in (1, 2, 3):
+    for ctas in (1, 2, 3, 4):
         _lib.check(_lib.lib.b200bls_set_ctas_per_sm(ctas))
         best = 1e9
         for _ in range(3):

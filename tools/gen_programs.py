@@ -18,6 +18,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "python-bls_b200"))
 from bls_b200.programs import registry                        # noqa: E402
+from bls_b200.vm import isa                                   # noqa: E402
 
 
 def main(out_path=None):
@@ -29,12 +30,17 @@ def main(out_path=None):
             name = "%s@%d" % (base, ctas)
             t = time.time()
             asm = None
-            for tm in ((n_tmem, 0) if n_tmem else (0,)):
+            for tm in ((n_tmem,) if ctas in registry.WIDE_SHAPES else (n_tmem, 0) if n_tmem else (0,)):
                 try:
                     asm = builder().assemble(n_slots, n_cold=4096, n_tmem=tm)
                     break
                 except RuntimeError as e:
                     err = e
+            if asm is not None and ctas in registry.WIDE_SHAPES:
+                # block-level reductions are written for 128-thread CTAs
+                ops = set(int(o) & 0xff for o in asm.code[:, 0])
+                if ops & {isa.OPCODE["SYNC"], isa.OPCODE["XMOV2"], isa.OPCODE["STRAWB2"]}:
+                    asm, err = None, "cross-thread program (128-thread CTAs only)"
             if asm is None:
                 if ctas == 1:
                     raise err
