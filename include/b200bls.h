@@ -156,6 +156,15 @@ int b200bls_g1_sum(const uint8_t* pts, uint8_t* out, size_t n);
 int b200bls_g1_sum_dev(const void* pts, void* out, size_t n);
 int b200bls_g2_sum(const uint8_t* pts, uint8_t* out, size_t n);
 int b200bls_g2_sum_dev(const void* pts, void* out, size_t n);
+/* Multi-scalar multiplication sum_i k_i * P_i -> one point: the secure aggregation folds
+ * sum T_i * sig_i (bls.py:29-56, 132-144) and sum T_i * pk_i (bls.py:217-221), where the reference
+ * runs one double-and-add ladder per point and a left fold.  pts: n affine points, scalars:
+ * n x 32 big-endian bytes.  Bucket method (11-bit windows, counting sort, one thread per
+ * bucket) from 65,536 points up, per-point ladders + reduction below.  n = 0 gives infinity. */
+int b200bls_g1_msm(const uint8_t* pts, const uint8_t* scalars, uint8_t* out, size_t n);
+int b200bls_g1_msm_dev(const void* pts, const void* scalars, void* out, size_t n);
+int b200bls_g2_msm(const uint8_t* pts, const uint8_t* scalars, uint8_t* out, size_t n);
+int b200bls_g2_msm_dev(const void* pts, const void* scalars, void* out, size_t n);
 /* PublicKey.from_bytes (keys.py:29-40) / Signature.from_bytes (signature.py:22-38):
  * compressed 48 / 96 bytes -> affine 96 / 192 bytes.  ok[i] = 0 (and a zero point) where the
  * reference raises ValueError('No sqrt exists' / 'No y for point x'). */
@@ -169,6 +178,12 @@ int b200bls_g2_compress_batch(const uint8_t* in, uint8_t* out, size_t n);
 /* hash_to_point_prehashed_Fq2 (ec.py:528-550): n x 32-byte message hashes -> n x 192 bytes. */
 int b200bls_hash_to_g2_batch(const uint8_t* hashes, uint8_t* out, size_t n);
 int b200bls_hash_to_g2_batch_dev(const void* hashes, void* out, size_t n);
+/* hash_pks (util.py:36-50), the per-key part: out[i] = SHA256(uint32_be(first_index + i) ||
+ * pk_hash) mod n as 32 big-endian bytes (the scalar format of the scalar-multiplication entry
+ * points), pk_hash = SHA256(pk_1 || ... || pk_N) computed by the caller.  These are the
+ * exponents T_i of secure aggregation (bls.py:29-56, 132-144, 217-221). */
+int b200bls_hash_pks(const uint8_t* pk_hash32, uint32_t first_index, uint8_t* out, size_t n);
+int b200bls_hash_pks_dev(const void* pk_hash32, uint32_t first_index, void* out, size_t n);
 /* n independent single-message verifications, the data-parallel core of BLS.verify
  * (bls.py:154-201): ok[i] = (e(-G1, sig_i) * e(pk_i, H(mh_i)) == 1).
  * pk: n x 96, mh: n x 32, sig: n x 192 (affine), ok: n bytes. */

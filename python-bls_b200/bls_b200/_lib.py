@@ -70,6 +70,12 @@ def _load():
         "b200bls_g2_decompress_batch": (i32, [vp, vp, vp, sz]),
         "b200bls_g1_compress_batch": (i32, [vp, vp, sz]),
         "b200bls_g2_compress_batch": (i32, [vp, vp, sz]),
+        "b200bls_g1_msm": (i32, [vp, vp, vp, sz]),
+        "b200bls_g1_msm_dev": (i32, [vp, vp, vp, sz]),
+        "b200bls_g2_msm": (i32, [vp, vp, vp, sz]),
+        "b200bls_g2_msm_dev": (i32, [vp, vp, vp, sz]),
+        "b200bls_hash_pks": (i32, [vp, ctypes.c_uint32, vp, sz]),
+        "b200bls_hash_pks_dev": (i32, [vp, ctypes.c_uint32, vp, sz]),
         "b200bls_hash_to_g2_batch": (i32, [vp, vp, sz]),
         "b200bls_hash_to_g2_batch_dev": (i32, [vp, vp, sz]),
         "b200bls_verify_batch": (i32, [vp, vp, vp, vp, sz]),

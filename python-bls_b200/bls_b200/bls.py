@@ -8,7 +8,7 @@ from . import ec, engine
 from .aggregation_info import AggregationInfo
 from .keys import PrivateKey, PublicKey
 from .signature import Signature
-from .util import GROUP_ORDER, hash_pks
+from .util import GROUP_ORDER, hash_pks, hash_pks_bytes
 
 
 class BLS:
@@ -23,9 +23,8 @@ class BLS:
         if not (len(signatures) == len(public_keys) == len(message_hashes)):
             raise Exception("Invalid number of keys")
         order = sorted(range(len(signatures)), key=lambda i: (message_hashes[i], public_keys[i], signatures[i]))
-        ts = hash_pks(len(public_keys), public_keys)
-        pts = ec.scalar_mul_many([signatures[i].value for i in order], ts, True)
-        return Signature.from_g2(ec.sum_points(pts, True))
+        ts = hash_pks_bytes(len(public_keys), public_keys)
+        return Signature.from_g2(ec.weighted_sum([signatures[i].value for i in order], ts, True))
 
     @staticmethod
     def aggregate_sigs(signatures):
@@ -50,9 +49,9 @@ class BLS:
         hit.sort(key=lambda s: s.aggregation_info)
         keys = sorted((mh, pk) for s in hit
                       for mh, pk in zip(s.aggregation_info.message_hashes, s.aggregation_info.public_keys))
-        ts = hash_pks(len(hit), [pk for _, pk in keys])
-        pts = ec.scalar_mul_many([s.value for s in hit], ts, True) + [s.value for s in rest]
-        final = Signature.from_g2(ec.sum_points(pts, True))
+        ts = hash_pks_bytes(len(hit), [pk for _, pk in keys])
+        secure_part = ec.weighted_sum([s.value for s in hit], ts, True)
+        final = Signature.from_g2(ec.sum_points([secure_part] + [s.value for s in rest], True))
         final.set_aggregation_info(AggregationInfo.merge_infos(infos))
         return final
 
@@ -104,7 +103,7 @@ class BLS:
         public_keys.sort()
         pts = [pk.value for pk in public_keys]
         if secure:
-            pts = ec.scalar_mul_many(pts, hash_pks(len(public_keys), public_keys), False)
+            return PublicKey.from_g1(ec.weighted_sum(pts, hash_pks_bytes(len(public_keys), public_keys), False))
         return PublicKey.from_g1(ec.sum_points(pts, False))
 
     @staticmethod

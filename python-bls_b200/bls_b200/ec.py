@@ -147,6 +147,16 @@ def sum_points(points, g2):
     return Point(engine.point_sum(b"".join(p.raw for p in points), g2).tobytes(), g2)
 
 
+def weighted_sum(points, scalars, g2):
+    """sum_i k_i * P_i in one multi-scalar multiplication on the GPU.  `scalars`: ints, or
+    already n x 32 big-endian bytes (e.g. straight from engine.hash_pks)."""
+    if not points:
+        return infinity(g2)
+    if not isinstance(scalars, (bytes, bytearray, np.ndarray)):
+        scalars = b"".join((int(k) % N).to_bytes(32, "big") for k in scalars)
+    return Point(engine.msm(b"".join(p.raw for p in points), scalars, g2).tobytes(), g2)
+
+
 def scalar_mul_many(points, scalars, g2):
     """[k_i * P_i] in one batched call"""
     if not points:

@@ -149,6 +149,29 @@ def compress(points, g2):
     return out
 
 
+def msm(points, scalars, g2):
+    """sum_i k_i * P_i: n affine points x n 32-byte big-endian scalars -> one affine point"""
+    _lib.init()
+    name, w = _g(g2)
+    points, scalars = as_u8(points), as_u8(scalars)
+    n = points.size // w
+    if points.size != n * w or scalars.size != n * 32:
+        raise ValueError("bad buffer sizes")
+    out = np.empty(w, dtype=np.uint8)
+    check(getattr(lib, "b200bls_%s_msm" % name)(ptr(points), ptr(scalars), ptr(out), n))
+    return out
+
+
+def hash_pks(pk_hash, n, first=0):
+    """aggregation exponents T_first .. T_(first+n-1) = SHA256(i || pk_hash) mod n -> n x 32 bytes
+    (the per-key part of bls_py.util.hash_pks, util.py:46-49)"""
+    _lib.init()
+    pk_hash = as_u8(pk_hash, 32)
+    out = np.empty(n * 32, dtype=np.uint8)
+    check(lib.b200bls_hash_pks(ptr(pk_hash), first, ptr(out), n))
+    return out
+
+
 def hash_to_g2(hashes):
     """n x 32-byte message hashes -> n x 192 bytes (hash_to_point_prehashed_Fq2)"""
     _lib.init()

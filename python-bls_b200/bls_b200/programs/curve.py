@@ -291,6 +291,37 @@ def build_sum_pass2(g2):
     return build
 
 
+def build_bucket_fold(g2):
+    """One bucket of the multi-scalar multiplication per thread (segmented launch mode of the
+    kernel): buffers 0 = affine points, read through the sorted index list, 1 = out, one affine
+    bucket sum per thread.  The accumulator stays Jacobian across the segment; one inversion per
+    bucket at the end.  Used by secure aggregation, sum_i T_i * P_i (bls_py/bls.py:29-56,
+    132-144, 217-221)."""
+    def build():
+        prog = Program("g2_bucket" if g2 else "g1_bucket")
+        c = Curve(prog, g2)
+        inf0 = c.infinity()
+        if g2:
+            acc = [prog.var2(v) for v in inf0]
+        else:
+            acc = [prog.var2(prog.pack(v, v)) for v in inf0]
+        prog.begin_body()
+        x, y, inf = c.load_affine(0)
+        inf = inf | ~prog.flag_active()
+        cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
+        s = c.add(cur, (x, y), mixed=True, inf2=inf)
+        for a, v in zip(acc, s):
+            if g2:
+                prog.assign(a, v)
+            else:
+                prog.emit("MOV1", a.c0, v)
+        prog.begin_epilogue()
+        cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
+        c.store_affine(1, 0, c.to_affine(cur))
+        return prog
+    return build
+
+
 def build_decompress(g2):
     """Signature.from_bytes (bls_py/signature.py:22-38) / PublicKey.from_bytes
     (bls_py/keys.py:29-40): compressed x with the 'big y' flag in the top bit ->

@@ -36,5 +36,6 @@ for _g2 in (False, True):
     PROGRAMS[_p + "_add"] = curve.build_add(_g2)
     PROGRAMS[_p + "_sum1"] = curve.build_sum_pass1(_g2)
     PROGRAMS[_p + "_sum2"] = curve.build_sum_pass2(_g2)
+    PROGRAMS[_p + "_bucket"] = curve.build_bucket_fold(_g2)
     PROGRAMS[_p + "_decompress"] = curve.build_decompress(_g2)
     PROGRAMS[_p + "_cflag"] = curve.build_compress_flag(_g2)

@@ -31,6 +31,22 @@ def hmac256(m, k):
     return hash256(bytes(x ^ 0x5c for x in k) + inner)
 
 
+DEVICE_HASH_PKS_MIN = 2048     # from this many exponents on, the per-key hashes run on the GPU
+
+
+def hash_pks_bytes(num_outputs, public_keys):
+    """hash_pks as num_outputs x 32 big-endian bytes (the scalar format of the GPU entry points).
+    The hash over all keys is one sequential SHA-256 (host); the num_outputs per-key hashes and
+    reductions mod n are independent and run on the GPU when there are many (row f2)."""
+    blob = b"".join(pk if isinstance(pk, (bytes, bytearray)) else pk.serialize() for pk in public_keys)
+    pk_hash = hash256(blob)
+    if num_outputs >= DEVICE_HASH_PKS_MIN:
+        from . import engine
+        return engine.hash_pks(pk_hash, num_outputs).tobytes()
+    return b"".join((int.from_bytes(hash256(i.to_bytes(4, "big") + pk_hash), "big") % GROUP_ORDER).to_bytes(32, "big")
+                    for i in range(num_outputs))
+
+
 def hash_pks(num_outputs, public_keys):
     """aggregation exponents T_i = H(i || H(pk_1 || ... || pk_n)) mod n (bls_py/util.py:36-50).
     `public_keys` are PublicKey objects or already-serialised 48-byte strings."""

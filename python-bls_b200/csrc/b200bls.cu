@@ -76,7 +76,7 @@ struct StreamCtx {
   size_t cold_bytes = 0;
   int* counters = nullptr;   // ring of item-block counters, one per launch in flight
   unsigned counter_pos = 0;
-  Staging scratch[6];        // device-side intermediates of multi-stage entry points
+  Staging scratch[12];       // device-side intermediates of multi-stage entry points
   Staging staging[VM_MAX_BUFS];  // device copies of the caller's host buffers
 };
 constexpr int N_COUNTERS = 256;
@@ -116,9 +116,16 @@ int ensure_buf(Staging& s, size_t bytes) {
 }
 
 // grid: ctas_per_sm CTAs per SM at most; fewer when the batch is small
-int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int n_bufs, int grid_override = 0) {
+struct SegArgs {
+  const unsigned* start;  // n_items + 1 offsets
+  const unsigned* idx;
+};
+
+int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int n_bufs, int grid_override = 0,
+                   const SegArgs* seg = nullptr) {
   Context& c = g_ctx;
   const int nt = pr.threads;
+  if (seg) grid_override = (int)((n_items + nt - 1) / nt);  // one thread per segment, statically assigned
   long long blocks_needed = (long long)((n_items + nt - 1) / nt);
   long long max_grid = (long long)c.sm_count * pr.ctas;
   int grid = (int)(blocks_needed < max_grid ? blocks_needed : max_grid);
@@ -151,6 +158,10 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   p.n_items = (long long)n_items;
   p.n_blocks = (long long)((n_items + nt - 1) / nt);
   p.counter = counter;
+  if (seg) {
+    p.seg_start = seg->start;
+    p.seg_idx = seg->idx;
+  }
   p.smem_cells = 2 * pr.n_slots;
   for (int i = 0; i < n_bufs && i < VM_MAX_BUFS; i++) p.bufs[i] = bufs[i];
   size_t smem = (size_t)pr.n_slots * 2 * 3 * sizeof(uint4) * nt;
@@ -310,6 +321,136 @@ int sum_dev(bool g2, const void* pts, void* out, size_t n) {
   return launch_named(n2, (size_t)grid, b2, 2, 1);
 }
 
+// ---- multi-scalar multiplication sum_i k_i P_i (secure aggregation, bls.py:29-56, 132-144,
+// 217-221): bucket method.  Scalars are cut into MSM_W windows of MSM_C bits; a counting sort
+// groups the (point, window) pairs by bucket = (window, digit); one thread per bucket folds
+// its points (g?_bucket program, segmented launch); the bucket sums are then multiplied by
+// digit << (MSM_C * window) with the ordinary scalar-multiplication program and summed by the
+// ordinary reduction.  24 mixed additions per point instead of 255 doublings + ~128 additions.
+constexpr int MSM_C = 11;
+constexpr int MSM_W = 24;                  // 24 * 11 = 264 >= 256 bits
+constexpr int MSM_B = MSM_W << MSM_C;      // 49,152 buckets (digit 0 stays empty)
+constexpr size_t MSM_MIN_N = 65536;        // below this the per-point ladder is as fast
+
+__device__ __forceinline__ unsigned msm_digit(const uint8_t* sc, int w) {
+  const int lo = w * MSM_C, byte = lo >> 3;
+  unsigned v = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    if (byte + k < 32) v |= (unsigned)sc[31 - (byte + k)] << (8 * k);  // scalars are big-endian
+  return (v >> (lo & 7)) & ((1u << MSM_C) - 1);
+}
+
+__global__ void msm_count_kernel(const uint8_t* __restrict__ scalars, unsigned* __restrict__ count, long long n) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * MSM_W) return;
+  const long long i = t / MSM_W;
+  const int w = (int)(t % MSM_W);
+  const unsigned d = msm_digit(scalars + i * 32, w);
+  if (d) atomicAdd(count + ((unsigned)w << MSM_C) + d, 1u);
+}
+
+// exclusive scan of count[MSM_B] -> start[MSM_B + 1]; one block of 1024 threads; clears count
+// so that the scatter pass can reuse it as the per-bucket cursor
+__global__ void msm_scan_kernel(unsigned* __restrict__ count, unsigned* __restrict__ start) {
+  constexpr int PER = MSM_B / 1024;
+  __shared__ unsigned part[1024];
+  const int t = threadIdx.x;
+  unsigned local[PER];
+  unsigned sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    local[k] = count[t * PER + k];
+    sum += local[k];
+    count[t * PER + k] = 0;
+  }
+  part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    unsigned v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  unsigned run = part[t] - sum;
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    start[t * PER + k] = run;
+    run += local[k];
+  }
+  if (t == 1023) start[MSM_B] = run;
+}
+
+__global__ void msm_scatter_kernel(const uint8_t* __restrict__ scalars, const unsigned* __restrict__ start,
+                                   unsigned* __restrict__ cursor, unsigned* __restrict__ idx, long long n) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * MSM_W) return;
+  const long long i = t / MSM_W;
+  const int w = (int)(t % MSM_W);
+  const unsigned d = msm_digit(scalars + i * 32, w);
+  if (!d) return;
+  const unsigned b = ((unsigned)w << MSM_C) + d;
+  idx[start[b] + atomicAdd(cursor + b, 1u)] = (unsigned)i;
+}
+
+// bucket scalars digit << (MSM_C * window) as 32 big-endian bytes
+__global__ void msm_bucket_scalars_kernel(uint8_t* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= MSM_B) return;
+  const int w = b >> MSM_C, lo = w * MSM_C;
+  const unsigned long long d = (unsigned long long)(b & ((1 << MSM_C) - 1)) << (lo & 7);
+  uint8_t* o = out + (size_t)b * 32;
+  for (int k = 0; k < 32; k++) o[k] = 0;
+  for (int k = 0; k < 3; k++)
+    if ((lo >> 3) + k < 32) o[31 - ((lo >> 3) + k)] = (uint8_t)(d >> (8 * k));
+}
+
+int msm_dev(bool g2, const void* pts, const void* scalars, void* out, size_t n) {
+  NEED_READY();
+  const size_t w = g2 ? 192 : 96;
+  const char* mul = g2 ? "g2_mul" : "g1_mul";
+  if (n >= 0xffffffffull / MSM_W) return fail(B200BLS_E_ARG, "msm: too many points");
+  if (n < MSM_MIN_N) {  // per-point ladder, then the reduction
+    if (n == 0) return sum_dev(g2, pts, out, 0);
+    int rc = ensure_scratch(6, w * n);
+    if (rc) return rc;
+    VmBuf b[3] = {vb(pts, (long long)w), vb(scalars, 32), vb(cur().scratch[6].ptr, (long long)w)};
+    rc = launch_named(mul, n, b, 3);
+    if (rc) return rc;
+    return sum_dev(g2, cur().scratch[6].ptr, out, n);
+  }
+  int rc = ensure_scratch(6, w * MSM_B);                                  // bucket sums, then their multiples
+  if (!rc) rc = ensure_scratch(7, sizeof(unsigned) * (size_t)MSM_B);      // counts / cursors
+  if (!rc) rc = ensure_scratch(8, sizeof(unsigned) * ((size_t)MSM_B + 1));  // segment offsets
+  if (!rc) rc = ensure_scratch(9, sizeof(unsigned) * n * MSM_W);          // point indices grouped by bucket
+  if (!rc) rc = ensure_scratch(10, (size_t)32 * MSM_B);                   // bucket scalars
+  if (!rc) rc = ensure_scratch(11, w * MSM_B);
+  if (rc) return rc;
+  StreamCtx& sc = cur();
+  unsigned* count = (unsigned*)sc.scratch[7].ptr;
+  unsigned* start = (unsigned*)sc.scratch[8].ptr;
+  unsigned* idx = (unsigned*)sc.scratch[9].ptr;
+  const long long pairs = (long long)n * MSM_W;
+  const unsigned pair_grid = (unsigned)((pairs + 255) / 256);
+  CU(cudaMemsetAsync(count, 0, sizeof(unsigned) * MSM_B, STREAM));
+  msm_count_kernel<<<pair_grid, 256, 0, STREAM>>>((const uint8_t*)scalars, count, (long long)n);
+  msm_scan_kernel<<<1, 1024, 0, STREAM>>>(count, start);
+  msm_scatter_kernel<<<pair_grid, 256, 0, STREAM>>>((const uint8_t*)scalars, start, count, idx, (long long)n);
+  msm_bucket_scalars_kernel<<<(MSM_B + 255) / 256, 256, 0, STREAM>>>((uint8_t*)sc.scratch[10].ptr);
+  CU(cudaGetLastError());
+  g_ctx.launches += 4;
+  const DevProgram* fold = find_program(g2 ? "g2_bucket" : "g1_bucket", MSM_B);
+  if (!fold) return B200BLS_E_PROGRAM;
+  SegArgs seg = {start, idx};
+  VmBuf bf[2] = {vb(pts, (long long)w), vb(sc.scratch[6].ptr, (long long)w)};
+  rc = launch_program(*fold, MSM_B, bf, 2, 0, &seg);
+  if (rc) return rc;
+  VmBuf bm[3] = {vb(sc.scratch[6].ptr, (long long)w), vb(sc.scratch[10].ptr, 32), vb(sc.scratch[11].ptr, (long long)w)};
+  rc = launch_named(mul, MSM_B, bm, 3);
+  if (rc) return rc;
+  return sum_dev(g2, sc.scratch[11].ptr, out, MSM_B);
+}
+
 // ---- multi-pairing: Miller loops -> raw Fq12 per item -> product tree ------------------------
 // out576: big-endian product of the Miller values (not final-exponentiated)
 int miller_product_dev(const void* P, const void* Q, void* out576, size_t n) {
@@ -337,6 +478,18 @@ int sha_stage_dev(const void* hashes, void* out256, size_t n) {
   int block = 256;
   long long grid = (threads + block - 1) / block;
   sha_stage_kernel<<<(unsigned)grid, block, 0, STREAM>>>((const uint8_t*)hashes, (uint8_t*)out256, (long long)n);
+  CU(cudaGetLastError());
+  g_ctx.launches++;
+  return 0;
+}
+
+// aggregation exponents T_i = H(i || pk_hash) mod n for i in [first, first + n) (util.py:46-49)
+int hash_pks_dev(const void* pk_hash32, uint32_t first, void* out, size_t n) {
+  NEED_READY();
+  if (n == 0) return 0;
+  int block = 256;
+  long long grid = ((long long)n + block - 1) / block;
+  hash_pks_kernel<<<(unsigned)grid, block, 0, STREAM>>>((const uint8_t*)pk_hash32, first, (uint8_t*)out, (long long)n);
   CU(cudaGetLastError());
   g_ctx.launches++;
   return 0;
@@ -819,6 +972,38 @@ int b200bls_hash_to_g2_batch(const uint8_t* hashes, uint8_t* out, size_t n) {
 int b200bls_hash_to_g2_batch_dev(const void* hashes, void* out, size_t n) {
   std::lock_guard<std::mutex> lk(g_mu);
   return hash_to_g2_dev(hashes, out, n);
+}
+int b200bls_g1_msm(const uint8_t* pts, const uint8_t* scalars, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out || (n && (!pts || !scalars))) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[3] = {{pts, nullptr, 96 * n}, {scalars, nullptr, 32 * n}, {nullptr, out, 96}};
+  return with_staging(io, 3, [&](void** d) { return msm_dev(false, d[0], d[1], d[2], n); });
+}
+int b200bls_g1_msm_dev(const void* pts, const void* scalars, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return msm_dev(false, pts, scalars, out, n);
+}
+int b200bls_g2_msm(const uint8_t* pts, const uint8_t* scalars, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out || (n && (!pts || !scalars))) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[3] = {{pts, nullptr, 192 * n}, {scalars, nullptr, 32 * n}, {nullptr, out, 192}};
+  return with_staging(io, 3, [&](void** d) { return msm_dev(true, d[0], d[1], d[2], n); });
+}
+int b200bls_g2_msm_dev(const void* pts, const void* scalars, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return msm_dev(true, pts, scalars, out, n);
+}
+int b200bls_hash_pks(const uint8_t* pk_hash32, uint32_t first_index, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!pk_hash32 || !out) return fail(B200BLS_E_ARG, "null buffer");
+  if ((unsigned long long)first_index + n > 0x100000000ull) return fail(B200BLS_E_ARG, "index does not fit 4 bytes");
+  HostIO io[2] = {{pk_hash32, nullptr, 32}, {nullptr, out, 32 * n}};
+  return with_staging(io, 2, [&](void** d) { return hash_pks_dev(d[0], first_index, d[1], n); });
+}
+int b200bls_hash_pks_dev(const void* pk_hash32, uint32_t first_index, void* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if ((unsigned long long)first_index + n > 0x100000000ull) return fail(B200BLS_E_ARG, "index does not fit 4 bytes");
+  return hash_pks_dev(pk_hash32, first_index, out, n);
 }
 int b200bls_miller_product(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n) {
   std::lock_guard<std::mutex> lk(g_mu);

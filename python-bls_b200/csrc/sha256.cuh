@@ -40,20 +40,10 @@ __host__ __device__ __forceinline__ constexpr uint32_t sha_k(int i) {
 
 SHA_HD uint32_t sha_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
-// one compression of a single padded block holding `h` (32 bytes), a 7-byte label and one
-// suffix byte; digest written big-endian to out[0..31].  The message schedule is a rolling
-// 16-word window and every loop is fully unrolled, so everything lives in registers.
-SHA_HD void sha256_h_label(const uint8_t* h, int j, int k, int suffix, uint8_t* out) {
-  uint32_t w[16];
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-    w[i] = ((uint32_t)h[4 * i] << 24) | ((uint32_t)h[4 * i + 1] << 16) | ((uint32_t)h[4 * i + 2] << 8) | h[4 * i + 3];
-  // label "G2_j_ck" then the suffix byte, then 0x80 padding and the bit length (40 bytes)
-  w[8] = ((uint32_t)'G' << 24) | ((uint32_t)'2' << 16) | ((uint32_t)'_' << 8) | (uint32_t)('0' + j);
-  w[9] = ((uint32_t)'_' << 24) | ((uint32_t)'c' << 16) | ((uint32_t)('0' + k) << 8) | (uint32_t)suffix;
-  w[10] = 0x80000000u;
-  w[11] = w[12] = w[13] = w[14] = 0;
-  w[15] = 40 * 8;
+// SHA-256 of ONE already padded 64-byte block given as 16 big-endian words (overwritten: the
+// message schedule is a rolling 16-word window); digest words to r[0..7].  Every loop is fully
+// unrolled, so everything lives in registers.
+SHA_HD void sha256_single_block(uint32_t* w, uint32_t* r) {
   uint32_t a = 0x6a09e667, b = 0xbb67ae85, c = 0x3c6ef372, d = 0xa54ff53a;
   uint32_t e = 0x510e527f, f = 0x9b05688c, g = 0x1f83d9ab, hh = 0x5be0cd19;
 #pragma unroll
@@ -72,8 +62,65 @@ SHA_HD void sha256_h_label(const uint8_t* h, int j, int k, int suffix, uint8_t* 
     uint32_t t2 = S0 + mj;
     hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
   }
-  const uint32_t r[8] = {0x6a09e667 + a, 0xbb67ae85 + b, 0x3c6ef372 + c, 0xa54ff53a + d,
-                         0x510e527f + e, 0x9b05688c + f, 0x1f83d9ab + g, 0x5be0cd19 + hh};
+  r[0] = 0x6a09e667 + a; r[1] = 0xbb67ae85 + b; r[2] = 0x3c6ef372 + c; r[3] = 0xa54ff53a + d;
+  r[4] = 0x510e527f + e; r[5] = 0x9b05688c + f; r[6] = 0x1f83d9ab + g; r[7] = 0x5be0cd19 + hh;
+}
+
+// one compression of a single padded block holding `h` (32 bytes), a 7-byte label and one
+// suffix byte; digest written big-endian to out[0..31].
+SHA_HD void sha256_h_label(const uint8_t* h, int j, int k, int suffix, uint8_t* out) {
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    w[i] = ((uint32_t)h[4 * i] << 24) | ((uint32_t)h[4 * i + 1] << 16) | ((uint32_t)h[4 * i + 2] << 8) | h[4 * i + 3];
+  // label "G2_j_ck" then the suffix byte, then 0x80 padding and the bit length (40 bytes)
+  w[8] = ((uint32_t)'G' << 24) | ((uint32_t)'2' << 16) | ((uint32_t)'_' << 8) | (uint32_t)('0' + j);
+  w[9] = ((uint32_t)'_' << 24) | ((uint32_t)'c' << 16) | ((uint32_t)('0' + k) << 8) | (uint32_t)suffix;
+  w[10] = 0x80000000u;
+  w[11] = w[12] = w[13] = w[14] = 0;
+  w[15] = 40 * 8;
+  uint32_t r[8];
+  sha256_single_block(w, r);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    out[4 * i] = (uint8_t)(r[i] >> 24);
+    out[4 * i + 1] = (uint8_t)(r[i] >> 16);
+    out[4 * i + 2] = (uint8_t)(r[i] >> 8);
+    out[4 * i + 3] = (uint8_t)r[i];
+  }
+}
+
+// group order n of BLS12-381, big-endian words
+#define B200BLS_N_WORDS \
+  {0x73eda753u, 0x299d7d48u, 0x3339d808u, 0x09a1d805u, 0x53bda402u, 0xfffe5bfeu, 0xffffffffu, 0x00000001u}
+
+// Aggregation exponent T_i = SHA256(i as 4 big-endian bytes || pk_hash) mod n (bls_py/util.py:
+// 46-49): one 36-byte single-block hash, then at most two subtractions of n (2^256 < 2.21 n).
+// pk_hash as 8 big-endian words; result as 32 big-endian bytes, the scalar format of the
+// scalar-multiplication programs.
+SHA_HD void hash_pks_exponent(uint32_t index, const uint32_t* pk_hash, uint8_t* out) {
+  const uint32_t nw[8] = B200BLS_N_WORDS;
+  uint32_t w[16], r[8];
+  w[0] = index;
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[1 + i] = pk_hash[i];
+  w[9] = 0x80000000u;
+  w[10] = w[11] = w[12] = w[13] = w[14] = 0;
+  w[15] = 36 * 8;
+  sha256_single_block(w, r);
+#pragma unroll
+  for (int round = 0; round < 2; round++) {
+    uint32_t d[8];
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {  // r - n, least significant word last in the array
+      uint64_t t = (uint64_t)r[i] - nw[i] - borrow;
+      d[i] = (uint32_t)t;
+      borrow = (uint32_t)(t >> 63);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : d[i];
+  }
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     out[4 * i] = (uint8_t)(r[i] >> 24);
@@ -93,6 +140,19 @@ __global__ void sha_stage_kernel(const uint8_t* __restrict__ hashes, uint8_t* __
   int sub = (int)(t & 7);
   int j = sub >> 2, k = (sub >> 1) & 1, suffix = sub & 1;
   sha256_h_label(hashes + item * 32, j, k, suffix, out + item * 256 + (j * 2 + k) * 64 + suffix * 32);
+}
+
+// T_first .. T_(first + n - 1), one thread each; out: n x 32 bytes
+__global__ void hash_pks_kernel(const uint8_t* __restrict__ pk_hash, uint32_t first, uint8_t* __restrict__ out,
+                                long long n) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint32_t h[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    h[i] = ((uint32_t)pk_hash[4 * i] << 24) | ((uint32_t)pk_hash[4 * i + 1] << 16) | ((uint32_t)pk_hash[4 * i + 2] << 8) |
+           pk_hash[4 * i + 3];
+  hash_pks_exponent(first + (uint32_t)t, h, out + t * 32);
 }
 #endif
 

@@ -37,6 +37,11 @@ struct VmParams {
   int smem_cells;          // cells [0, smem_cells) live in shared memory, the rest in Tensor Memory
   int tmem_cols;           // TMEM columns to allocate per CTA (0, 128, 256 or 512)
   int tmem_group_cols;     // columns owned by each group of four warps (CTAs wider than 128 threads)
+  // Segmented mode (multi-scalar multiplication buckets): thread t owns segment t of `n_items`
+  // segments; body iteration k processes record seg_idx[seg_start[t] + k] of the indexed buffers
+  // (inactive once k reaches the segment length); prologue / epilogue address record t.
+  const unsigned* seg_start;  // n_items + 1 offsets into seg_idx, or nullptr (normal mode)
+  const unsigned* seg_idx;
   VmBuf bufs[VM_MAX_BUFS];
 };
 
@@ -320,6 +325,30 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) vm_kernel(const __grid_constant_
   // batch is exhausted (CTAs that find no work left exit early, so the CTAs of the next launch
   // on another stream can move in: no tail-wave quantisation across back-to-back batches);
   // epilogue once.  One copy of the interpreter loop serves all three sections.
+  if (p.seg_start != nullptr) {
+    __shared__ unsigned s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    unsigned s0 = 0, len = 0;
+    if (gtid < p.n_items) {
+      s0 = __ldg(p.seg_start + gtid);
+      len = __ldg(p.seg_start + gtid + 1) - s0;
+    }
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, len);
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const unsigned iters = s_max;  // longest segment of this CTA
+    vm_run_section(env, p.code, 0, p.body_start);
+    for (unsigned k = 0; k < iters; k++) {
+      const bool act = k < len;
+      env.item = act ? (long long)__ldg(p.seg_idx + s0 + k) : 0;
+      env.item_raw = act ? 0 : p.n_items;  // FACTIVE reads item_raw < n_items
+      vm_run_section(env, p.code, p.body_start, p.epi_start);
+    }
+    env.item_raw = gtid;
+    env.item = gtid < last ? gtid : last;
+    vm_run_section(env, p.code, p.epi_start, p.n_ins);
+  } else
   for (int phase = 0; phase < 3;) {
     int lo, hi;
     if (phase == 0) {

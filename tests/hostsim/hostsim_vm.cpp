@@ -203,3 +203,12 @@ extern "C" void hs_sha_stage(const uint8_t* hashes, uint8_t* out, long n) {
       sha256_h_label(hashes + item * 32, j, k, suffix, out + item * 256 + (j * 2 + k) * 64 + suffix * 32);
     }
 }
+
+// aggregation exponents T_i (same function hash_pks_kernel runs per thread)
+extern "C" void hs_hash_pks(const uint8_t* pk_hash, uint32_t first, uint8_t* out, long n) {
+  uint32_t h[8];
+  for (int i = 0; i < 8; i++)
+    h[i] = ((uint32_t)pk_hash[4 * i] << 24) | ((uint32_t)pk_hash[4 * i + 1] << 16) | ((uint32_t)pk_hash[4 * i + 2] << 8) |
+           pk_hash[4 * i + 3];
+  for (long t = 0; t < n; t++) b200bls::hash_pks_exponent(first + (uint32_t)t, h, out + t * 32);
+}

@@ -1,6 +1,7 @@
 """CPU tests of the host-side scheme logic (no GPU needed): hashing helpers, aggregation
 exponents and AggregationInfo merging against vectors generated from the live reference."""
 import bls_oracle as O
+import pytest
 from conftest import load_golden
 
 from bls_b200 import ec, synth
@@ -72,3 +73,22 @@ def test_synthetic_inputs_are_reproducible():
     assert (synth.scalars(synth.SEED_PAIRING, 5) == s).all()
     bad = synth.corrupted_indices(7, 1000)
     assert len(bad) == 10 and len(set(bad.tolist())) == 10
+
+
+def test_lagrange_and_interpolation_match_reference():
+    """threshold.py:57-102 on the host (ints mod n), against values recorded from the reference"""
+    from bls_b200.threshold import Threshold
+    from bls_b200.util import GROUP_ORDER
+    for t in load_golden("ext_kat.json")["threshold"]:
+        X = t["players"]
+        lambs = Threshold.lagrange_coeffs_at_zero(X)
+        assert [hex(l) for l in lambs] == t["lagrange"]
+        shares = [int(s, 16) for s in t["shares"]]
+        assert Threshold.interpolate_at_zero(X, [shares[x - 1] for x in X]) == int(t["master_sk"], 16)
+    # P(x) = 7 + 3x + 5x^2 through three points
+    P = lambda x: (7 + 3 * x + 5 * x * x) % GROUP_ORDER
+    assert Threshold.interpolate_at_zero([2, 9, 11], [P(2), P(9), P(11)]) == 7
+    with pytest.raises(AssertionError):
+        Threshold.lagrange_coeffs_at_zero([1, 1])
+    with pytest.raises(AssertionError):
+        Threshold.lagrange_coeffs_at_zero([0, 1])

@@ -49,6 +49,28 @@ def test_sha_stage_matches_hashlib():
         assert raw[256 * i:256 * (i + 1)] == want
 
 
+def test_hash_pks_exponents_device_code():
+    """the per-key part of hash_pks (util.py:46-49) as the CUDA kernel computes it, against the
+    oracle and the reference's own exponents (agg_kat / sig_kat were produced with them)"""
+    lib = hostsim.lib()
+    pk_hash = O.hash256(b"some public keys")
+    n = 300
+    out = np.zeros(32 * n, dtype=np.uint8)
+    lib.hs_hash_pks(pk_hash, ctypes.c_uint32(0), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(n))
+    raw = out.tobytes()
+    for i in range(n):
+        want = int.from_bytes(O.hash256(i.to_bytes(4, "big") + pk_hash), "big") % O.N
+        assert int.from_bytes(raw[32 * i:32 * (i + 1)], "big") == want
+    # a digest >= 2n needs both subtractions, one in [n, 2n) one, one below n none: all three occur
+    vals = [int.from_bytes(O.hash256(i.to_bytes(4, "big") + pk_hash), "big") // O.N for i in range(n)]
+    assert set(vals) == {0, 1, 2}
+    # non-zero first index
+    lib.hs_hash_pks(pk_hash, ctypes.c_uint32(0xfffffff0), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(8))
+    for i in range(8):
+        want = int.from_bytes(O.hash256((0xfffffff0 + i).to_bytes(4, "big") + pk_hash), "big") % O.N
+        assert int.from_bytes(out.tobytes()[32 * i:32 * (i + 1)], "big") == want
+
+
 def test_hash_and_verify_programs():
     g = load_golden("hash_kat.json")
     cases = g["hash_to_g2_prehashed"][:6]

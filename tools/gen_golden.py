@@ -365,9 +365,112 @@ def agg_kat():
                           "secure_pk_agg": {"pks": [p.serialize().hex() for p in pks],
                                             "out": sec.serialize().hex()}})
 
+# ---------------------------------------------------------------------------
+def ext_kat():
+    """Signature.divide_by (signature.py:44-103), HD keys (keys.py:167-316) and
+    threshold signatures (threshold.py:57-136, keys.py:93-117, 137-147) -- recorded from the
+    live reference after its own test_vectors2 / test_vectors3 / test_threshold pass."""
+    from bls_py.keys import ExtendedPrivateKey, ExtendedPublicKey
+    from bls_py.threshold import Threshold
+    suite = unittest.TestSuite([ref_tests.TestBLS("test_vectors2"), ref_tests.TestBLS("test_vectors3"),
+                                ref_tests.TestBLS("test_threshold")])
+    res = unittest.TextTestRunner(verbosity=0).run(suite)
+    assert res.wasSuccessful()
+
+    # --- divide_by -------------------------------------------------------------------------
+    sk1 = PrivateKey.from_seed(bytes([1, 2, 3, 4, 5]))
+    sk2 = PrivateKey.from_seed(bytes([1, 2, 3, 4, 5, 6]))
+    m1, m2, m3, m4 = bytes([1, 2, 3, 40]), bytes([5, 6, 70, 201]), bytes([9, 10, 11, 12, 13]), bytes([15, 63, 244, 92, 0, 1])
+    sig1, sig2, sig3 = sk1.sign(m1), sk2.sign(m2), sk2.sign(m1)
+    sig4, sig5, sig6 = sk1.sign(m3), sk1.sign(m1), sk1.sign(m4)
+    sig_l = BLS.aggregate_sigs([sig1, sig2])
+    sig_r = BLS.aggregate_sigs([sig3, sig4, sig5])
+    sig_final = BLS.aggregate_sigs([sig_l, sig_r, sig6])
+    quotient = sig_final.divide_by([sig2, sig5, sig6])
+
+    def tree(sig):
+        return sorted([[k[0].hex(), k[1].serialize().hex(), hex(e)] for k, e in sig.aggregation_info.tree.items()])
+
+    def raises(fn):
+        try:
+            fn()
+            return False
+        except Exception:
+            return True
+
+    div = {"quotient": quotient.serialize().hex(), "quotient_tree": tree(quotient),
+           "verify_quotient": BLS.verify(quotient),
+           "divide_by_nothing_is_identity": quotient.divide_by([]) == quotient,
+           "not_subset_raises": raises(lambda: quotient.divide_by([sig6])),
+           "by_sig1": sig_final.divide_by([sig1]).serialize().hex(),
+           "not_unique_raises": raises(lambda: sig_final.divide_by([sig_l]))}
+    sig7, sig8 = sk2.sign(m3), sk2.sign(m4)
+    sig_r2 = BLS.aggregate_sigs([sig7, sig8])
+    sig_final2 = BLS.aggregate_sigs([sig_final, sig_r2])
+    quotient2 = sig_final2.divide_by([sig_r2])
+    div["sig_final2"] = sig_final2.serialize().hex()
+    div["quotient2"] = quotient2.serialize().hex()
+    div["quotient2_tree"] = tree(quotient2)
+    div["verify_quotient2"] = BLS.verify(quotient2)
+
+    # --- HD keys ----------------------------------------------------------------------------
+    seed = bytes([1, 50, 6, 244, 24, 199, 1, 25])
+    esk = ExtendedPrivateKey.from_seed(seed)
+    hd = {"seed": seed.hex(), "nodes": []}
+    paths = [[], [77 + 2 ** 31], [3], [3, 17], [0, 2 ** 31, 5], [2 ** 31 + 1, 2 ** 31 + 2]]
+    for path in paths:
+        node = esk
+        for i in path:
+            node = node.private_child(i)
+        epk = node.get_extended_public_key()
+        entry = {"path": path, "xprv": node.serialize().hex(), "xpub": epk.serialize().hex(),
+                 "fingerprint": node.get_public_key().get_fingerprint(), "chain_code": node.chain_code.hex()}
+        if all(i < 2 ** 31 for i in path):
+            pub = esk.get_extended_public_key()
+            for i in path:
+                pub = pub.public_child(i)
+            entry["xpub_public_derivation"] = pub.serialize().hex()
+        hd["nodes"].append(entry)
+    assert hd["nodes"][0]["fingerprint"] == 0xa4700b27 and hd["nodes"][3]["fingerprint"] == 0xff26a31f
+
+    # --- threshold: a deterministic 2-of-3 and 3-of-5 dealing (new_threshold's own steps, keys.py:109-117,
+    # with a seeded generator instead of the system RNG) ----------------------------------------
+    g1 = rec.generator_Fq()
+    rnd = random.Random(0x7E5801D)
+    thr = []
+    for T, NP in ((1, 1), (2, 3), (3, 5)):
+        polys = [[rnd.randrange(1, N) for _ in range(T)] for _ in range(NP)]
+        commitments = [[(g1 * c) for c in poly] for poly in polys]
+        frags = [[sum(c * pow(x, i, N) for i, c in enumerate(poly)) % N for x in range(1, NP + 1)] for poly in polys]
+        # fragments[target][source]
+        fragments = [[frags[src][tgt] for src in range(NP)] for tgt in range(NP)]
+        for src in range(1, NP + 1):
+            for tgt in range(1, NP + 1):
+                assert Threshold.verify_secret_fragment(T, Fq(N, fragments[tgt - 1][src - 1]), tgt, commitments[src - 1])
+        master_pk = BLS.aggregate_pub_keys([PublicKey.from_g1(c[0].to_jacobian()) for c in commitments], False)
+        shares = [BLS.aggregate_priv_keys([PrivateKey(f) for f in row], None, False) for row in fragments]
+        master_sk = BLS.aggregate_priv_keys([PrivateKey(p[0]) for p in polys], None, False)
+        msg = "Test"
+        sig_actual = master_sk.sign(msg)
+        X = list(range(1, NP + 1))[-T:]            # the last T players
+        lambs = [int(l) for l in Threshold.lagrange_coeffs_at_zero(X)]
+        sig_shares = [shares[x - 1].sign_threshold(msg, x, X) for x in X]
+        assert BLS.aggregate_sigs_simple(sig_shares) == sig_actual
+        unit = [shares[x - 1].sign(msg) for x in X]
+        assert Threshold.aggregate_unit_sigs(unit, X, T) == sig_actual
+        assert int(Threshold.interpolate_at_zero(X, [Fq(N, shares[x - 1].value) for x in X])) == master_sk.value
+        thr.append({"T": T, "N": NP, "polys": [[hex(c) for c in p] for p in polys],
+                    "commitments": [[c.serialize().hex() for c in cs] for cs in commitments],
+                    "fragments": [[hex(f) for f in row] for row in fragments],
+                    "master_pk": master_pk.serialize().hex(), "master_sk": master_sk.serialize().hex(),
+                    "shares": [s.serialize().hex() for s in shares], "players": X, "lagrange": [hex(l) for l in lambs],
+                    "sig_shares": [s.serialize().hex() for s in sig_shares],
+                    "unit_sigs": [s.serialize().hex() for s in unit], "signature": sig_actual.serialize().hex()})
+    dump("ext_kat.json", {"divide_by": div, "hd": hd, "threshold": thr})
+
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["field", "curve", "pairing", "hash", "sig", "agg"]
+    which = sys.argv[1:] or ["field", "curve", "pairing", "hash", "sig", "agg", "ext"]
     for w in which:
         globals()[w + "_kat"]()
