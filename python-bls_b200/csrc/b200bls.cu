@@ -5,6 +5,7 @@
 // buffers for the host-pointer entry points, and the launch logic.  No CPU compute path
 // exists here: every entry point either launches vm_kernel on the GPU or fails.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -323,10 +324,11 @@ int sum_dev(bool g2, const void* pts, void* out, size_t n) {
 
 // ---- multi-scalar multiplication sum_i k_i P_i (secure aggregation, bls.py:29-56, 132-144,
 // 217-221): bucket method.  Scalars are cut into MSM_W windows of MSM_C bits; a counting sort
-// groups the (point, window) pairs by bucket = (window, digit); one thread per bucket folds
-// its points (g?_bucket program, segmented launch); the bucket sums are then multiplied by
-// digit << (MSM_C * window) with the ordinary scalar-multiplication program and summed by the
-// ordinary reduction.  24 mixed additions per point instead of 255 doublings + ~128 additions.
+// groups the (point, window) pairs by bucket = (window, digit); buckets are cut into segments
+// of bounded length and one thread per segment folds its points (g?_bucket program, segmented
+// launch); the segment sums are then multiplied by digit << (MSM_C * window) with the ordinary
+// scalar-multiplication program and summed by the ordinary reduction.  24 mixed additions per
+// point instead of 255 doublings + ~128 additions.
 constexpr int MSM_C = 11;
 constexpr int MSM_W = 24;                  // 24 * 11 = 264 >= 256 bits
 constexpr int MSM_B = MSM_W << MSM_C;      // 49,152 buckets (digit 0 stays empty)
@@ -350,35 +352,68 @@ __global__ void msm_count_kernel(const uint8_t* __restrict__ scalars, unsigned* 
   if (d) atomicAdd(count + ((unsigned)w << MSM_C) + d, 1u);
 }
 
-// exclusive scan of count[MSM_B] -> start[MSM_B + 1]; one block of 1024 threads; clears count
-// so that the scatter pass can reuse it as the per-bucket cursor
-__global__ void msm_scan_kernel(unsigned* __restrict__ count, unsigned* __restrict__ start) {
+// exclusive scans over the MSM_B bucket counts, one block of 1024 threads:
+//   start[b]     offset of bucket b in the grouped index list (start[MSM_B] = number of pairs)
+//   seg_first[b] number of segments before bucket b, a bucket of c points being cut into
+//                ceil(c / seg_len) segments so that no thread folds more than seg_len points
+//                (scalars are caller data: a skewed digit distribution -- equal scalars, or the
+//                2-bit top window of a 255-bit scalar -- must not serialise the fold)
+// Clears count so that the scatter pass can reuse it as the per-bucket cursor.
+__global__ void __launch_bounds__(1024) msm_scan_kernel(unsigned* __restrict__ count, unsigned* __restrict__ start,
+                                unsigned* __restrict__ seg_first, unsigned seg_len) {
   constexpr int PER = MSM_B / 1024;
-  __shared__ unsigned part[1024];
+  __shared__ unsigned part[1024], part2[1024];
   const int t = threadIdx.x;
   unsigned local[PER];
-  unsigned sum = 0;
+  unsigned sum = 0, sum2 = 0;
 #pragma unroll
   for (int k = 0; k < PER; k++) {
     local[k] = count[t * PER + k];
     sum += local[k];
+    sum2 += (local[k] + seg_len - 1) / seg_len;
     count[t * PER + k] = 0;
   }
   part[t] = sum;
+  part2[t] = sum2;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {
-    unsigned v = t >= off ? part[t - off] : 0;
+    unsigned v = t >= off ? part[t - off] : 0, v2 = t >= off ? part2[t - off] : 0;
     __syncthreads();
     part[t] += v;
+    part2[t] += v2;
     __syncthreads();
   }
-  unsigned run = part[t] - sum;
+  unsigned run = part[t] - sum, run2 = part2[t] - sum2;
 #pragma unroll
   for (int k = 0; k < PER; k++) {
     start[t * PER + k] = run;
+    seg_first[t * PER + k] = run2;
     run += local[k];
+    run2 += (local[k] + seg_len - 1) / seg_len;
   }
-  if (t == 1023) start[MSM_B] = run;
+  if (t == 1023) {
+    start[MSM_B] = run;
+    seg_first[MSM_B] = run2;
+  }
+}
+
+// segment table: seg_start[s] = first position of segment s in the index list, seg_scalar[s] =
+// digit << (MSM_C * window) of its bucket as 32 big-endian bytes.  One thread per bucket.
+__global__ void msm_segments_kernel(const unsigned* __restrict__ start, const unsigned* __restrict__ seg_first,
+                                    unsigned seg_len, unsigned* __restrict__ seg_start, uint8_t* __restrict__ seg_scalar) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= MSM_B) return;
+  const unsigned s0 = seg_first[b], s1 = seg_first[b + 1];
+  const int w = b >> MSM_C, lo = w * MSM_C;
+  const unsigned long long d = (unsigned long long)(b & ((1 << MSM_C) - 1)) << (lo & 7);
+  for (unsigned s = s0; s < s1; s++) {
+    seg_start[s] = start[b] + (s - s0) * seg_len;
+    uint8_t* o = seg_scalar + (size_t)s * 32;
+    for (int k = 0; k < 32; k++) o[k] = 0;
+    for (int k = 0; k < 3; k++)
+      if ((lo >> 3) + k < 32) o[31 - ((lo >> 3) + k)] = (uint8_t)(d >> (8 * k));
+  }
+  if (b == MSM_B - 1) seg_start[s1] = start[MSM_B];
 }
 
 __global__ void msm_scatter_kernel(const uint8_t* __restrict__ scalars, const unsigned* __restrict__ start,
@@ -391,18 +426,6 @@ __global__ void msm_scatter_kernel(const uint8_t* __restrict__ scalars, const un
   if (!d) return;
   const unsigned b = ((unsigned)w << MSM_C) + d;
   idx[start[b] + atomicAdd(cursor + b, 1u)] = (unsigned)i;
-}
-
-// bucket scalars digit << (MSM_C * window) as 32 big-endian bytes
-__global__ void msm_bucket_scalars_kernel(uint8_t* __restrict__ out) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= MSM_B) return;
-  const int w = b >> MSM_C, lo = w * MSM_C;
-  const unsigned long long d = (unsigned long long)(b & ((1 << MSM_C) - 1)) << (lo & 7);
-  uint8_t* o = out + (size_t)b * 32;
-  for (int k = 0; k < 32; k++) o[k] = 0;
-  for (int k = 0; k < 3; k++)
-    if ((lo >> 3) + k < 32) o[31 - ((lo >> 3) + k)] = (uint8_t)(d >> (8 * k));
 }
 
 int msm_dev(bool g2, const void* pts, const void* scalars, void* out, size_t n) {
@@ -419,36 +442,49 @@ int msm_dev(bool g2, const void* pts, const void* scalars, void* out, size_t n) 
     if (rc) return rc;
     return sum_dev(g2, cur().scratch[6].ptr, out, n);
   }
-  int rc = ensure_scratch(6, w * MSM_B);                                  // bucket sums, then their multiples
-  if (!rc) rc = ensure_scratch(7, sizeof(unsigned) * (size_t)MSM_B);      // counts / cursors
-  if (!rc) rc = ensure_scratch(8, sizeof(unsigned) * ((size_t)MSM_B + 1));  // segment offsets
-  if (!rc) rc = ensure_scratch(9, sizeof(unsigned) * n * MSM_W);          // point indices grouped by bucket
-  if (!rc) rc = ensure_scratch(10, (size_t)32 * MSM_B);                   // bucket scalars
-  if (!rc) rc = ensure_scratch(11, w * MSM_B);
+  // longest run one thread folds: the mean bucket size plus seven standard deviations, so that
+  // uniformly distributed digits are never cut and skewed ones are spread over many threads
+  const double mean = (double)n / (1 << MSM_C);
+  const unsigned seg_len = (unsigned)(mean + 7.0 * sqrt(mean) + 16.0);
+  const long long pairs = (long long)n * MSM_W;
+  const size_t seg_cap = (size_t)MSM_B + (size_t)(pairs / seg_len) + 1;     // upper bound on the number of segments
+  int rc = ensure_scratch(6, w * seg_cap);                                  // segment sums
+  if (!rc) rc = ensure_scratch(7, sizeof(unsigned) * (size_t)MSM_B);        // counts / cursors
+  if (!rc) rc = ensure_scratch(8, sizeof(unsigned) * 2 * ((size_t)MSM_B + 1));  // bucket offsets, segment counts
+  if (!rc) rc = ensure_scratch(9, sizeof(unsigned) * (size_t)pairs);        // point indices grouped by bucket
+  if (!rc) rc = ensure_scratch(10, (size_t)36 * (seg_cap + 1));             // segment offsets + scalars
+  if (!rc) rc = ensure_scratch(11, w * seg_cap);                            // segment sums times bucket scalars
   if (rc) return rc;
   StreamCtx& sc = cur();
   unsigned* count = (unsigned*)sc.scratch[7].ptr;
   unsigned* start = (unsigned*)sc.scratch[8].ptr;
+  unsigned* seg_first = start + MSM_B + 1;
   unsigned* idx = (unsigned*)sc.scratch[9].ptr;
-  const long long pairs = (long long)n * MSM_W;
+  unsigned* seg_start = (unsigned*)sc.scratch[10].ptr;
+  uint8_t* seg_scalar = (uint8_t*)(seg_start + ((seg_cap + 1 + 7) & ~(size_t)7));
   const unsigned pair_grid = (unsigned)((pairs + 255) / 256);
   CU(cudaMemsetAsync(count, 0, sizeof(unsigned) * MSM_B, STREAM));
   msm_count_kernel<<<pair_grid, 256, 0, STREAM>>>((const uint8_t*)scalars, count, (long long)n);
-  msm_scan_kernel<<<1, 1024, 0, STREAM>>>(count, start);
+  msm_scan_kernel<<<1, 1024, 0, STREAM>>>(count, start, seg_first, seg_len);
   msm_scatter_kernel<<<pair_grid, 256, 0, STREAM>>>((const uint8_t*)scalars, start, count, idx, (long long)n);
-  msm_bucket_scalars_kernel<<<(MSM_B + 255) / 256, 256, 0, STREAM>>>((uint8_t*)sc.scratch[10].ptr);
+  msm_segments_kernel<<<(MSM_B + 255) / 256, 256, 0, STREAM>>>(start, seg_first, seg_len, seg_start, seg_scalar);
   CU(cudaGetLastError());
   g_ctx.launches += 4;
-  const DevProgram* fold = find_program(g2 ? "g2_bucket" : "g1_bucket", MSM_B);
+  unsigned n_seg = 0;
+  CU(cudaMemcpyAsync(&n_seg, seg_first + MSM_B, sizeof(unsigned), cudaMemcpyDeviceToHost, STREAM));
+  CU(cudaStreamSynchronize(STREAM));
+  if (n_seg == 0) return sum_dev(g2, pts, out, 0);  // every scalar is zero
+  if (n_seg > seg_cap) return fail(B200BLS_E_CUDA, "msm: segment count %u exceeds its bound %zu", n_seg, seg_cap);
+  const DevProgram* fold = find_program(g2 ? "g2_bucket" : "g1_bucket", n_seg);
   if (!fold) return B200BLS_E_PROGRAM;
-  SegArgs seg = {start, idx};
+  SegArgs seg = {seg_start, idx};
   VmBuf bf[2] = {vb(pts, (long long)w), vb(sc.scratch[6].ptr, (long long)w)};
-  rc = launch_program(*fold, MSM_B, bf, 2, 0, &seg);
+  rc = launch_program(*fold, n_seg, bf, 2, 0, &seg);
   if (rc) return rc;
-  VmBuf bm[3] = {vb(sc.scratch[6].ptr, (long long)w), vb(sc.scratch[10].ptr, 32), vb(sc.scratch[11].ptr, (long long)w)};
-  rc = launch_named(mul, MSM_B, bm, 3);
+  VmBuf bm[3] = {vb(sc.scratch[6].ptr, (long long)w), vb(seg_scalar, 32), vb(sc.scratch[11].ptr, (long long)w)};
+  rc = launch_named(mul, n_seg, bm, 3);
   if (rc) return rc;
-  return sum_dev(g2, sc.scratch[11].ptr, out, MSM_B);
+  return sum_dev(g2, sc.scratch[11].ptr, out, n_seg);
 }
 
 // ---- multi-pairing: Miller loops -> raw Fq12 per item -> product tree ------------------------

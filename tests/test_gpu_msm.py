@@ -99,6 +99,12 @@ def test_msm_buckets_identity(g2):
     want = ser(O.aff_mul(sum(k * e for k, e in zip(ks, es)) % N, G))
     got = engine.msm(pts, sc, g2).tobytes()
     assert got == want
+    # skewed digits: every scalar the same, so 24 buckets hold all the points (they are cut into
+    # bounded segments folded by different threads)
+    e0 = es[7] | 1
+    same = e0.to_bytes(32, "big") * n
+    assert engine.msm(pts, same, g2).tobytes() == ser(O.aff_mul(sum(ks) * e0 % N, G))
+    assert engine.msm(pts, bytes(32 * n), g2).tobytes() == bytes(w)          # all scalars zero
     # the ladder path on a slice agrees with the same identity (cross-check of both paths)
     m = 300
     assert engine.msm(pts[:m], sc[:32 * m], g2).tobytes() == \

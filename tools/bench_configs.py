@@ -78,6 +78,45 @@ for name, base, flag, G, ser in (("g2_signatures", g2, True, O.G2, ser2), ("g1_p
 out["config3_aggregate"] = res3
 print(json.dumps(res3), flush=True)
 
+# ---- config 3, secure variant (row f3): sum T_i * P_i with the aggregation exponents T_i ---------
+import hashlib                                              # noqa: E402
+pk_hash = hashlib.sha256(b"config 3 secure").digest()
+d_pkh = engine.DeviceBuffer(32).upload(np.frombuffer(pk_hash, dtype=np.uint8))
+d_T = engine.DeviceBuffer(32 * n3)
+ms_T = timed(lambda: check(lib.b200bls_hash_pks_dev(d_pkh.ptr, 0, d_T.ptr, n3)))
+T_host = d_T.download().reshape(n3, 32)
+t0 = time.perf_counter()
+T_ref = [int.from_bytes(hashlib.sha256(i.to_bytes(4, "big") + pk_hash).digest(), "big") % O.N for i in range(n3)]
+host_T_seconds = time.perf_counter() - t0
+ks = [int.from_bytes(bytes(r), "big") for r in sc]
+exp_ok = all(int.from_bytes(bytes(T_host[i]), "big") == T_ref[i] for i in range(0, n3, max(1, n3 // 5000)))
+dot = sum(k * t for k, t in zip(ks, T_ref)) % O.N
+res3s = {"n": n3, "exponents": {"ms_device": ms_T, "seconds_host_hashlib": host_T_seconds, "parity_sampled": bool(exp_ok)}}
+for name, base, flag, G, ser in (("g2_signatures", g2, True, O.G2, ser2), ("g1_public_keys", g1, False, O.G1, ser1)):
+    w = 192 if flag else 96
+    d_pts = dev_scalar_mul(base, sc, flag)
+    d_sum = engine.DeviceBuffer(w)
+    fn = lib.b200bls_g2_msm_dev if flag else lib.b200bls_g1_msm_dev
+    ms = timed(lambda: check(fn(d_pts.ptr, d_T.ptr, d_sum.ptr, n3)), reps=2)
+    got = d_sum.download().tobytes()
+    # the previous path: one ladder per point, then the reduction
+    d_mul = engine.DeviceBuffer(w * n3)
+    mul = lib.b200bls_g2_scalar_mul_batch_dev if flag else lib.b200bls_g1_scalar_mul_batch_dev
+    red = lib.b200bls_g2_sum_dev if flag else lib.b200bls_g1_sum_dev
+    d_sum2 = engine.DeviceBuffer(w)
+
+    def ladder():
+        check(mul(d_pts.ptr, d_T.ptr, d_mul.ptr, n3))
+        check(red(d_mul.ptr, d_sum2.ptr, n3))
+    ms_ladder = timed(ladder, reps=1)
+    res3s[name] = {"ms_msm": ms, "points_per_s": n3 / (ms * 1e-3), "ms_ladders_plus_sum": ms_ladder,
+                   "parity_identity": got == ser(O.aff_mul(dot, G)),
+                   "ladder_path_agrees": d_sum2.download().tobytes() == got}
+    d_pts.free()
+    d_mul.free()
+out["config3_secure_aggregate"] = res3s
+print(json.dumps(res3s), flush=True)
+
 # ---- config 4 -------------------------------------------------------------------------------
 n4 = int(10_000 * scale)
 sks = synth.scalars(synth.SEED_AGG_VERIFY, n4)
