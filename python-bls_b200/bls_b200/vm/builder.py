@@ -190,10 +190,10 @@ class Flag(Val):
 
 
 class VOp:
-    __slots__ = ("name", "d", "a", "b", "aux")
+    __slots__ = ("name", "d", "a", "b", "aux", "post")
 
-    def __init__(self, name, d, a, b, aux):
-        self.name, self.d, self.a, self.b, self.aux = name, d, a, b, aux
+    def __init__(self, name, d, a, b, aux, post=0):
+        self.name, self.d, self.a, self.b, self.aux, self.post = name, d, a, b, aux, post
 
 
 def _is_val(x):
@@ -413,10 +413,76 @@ class Assembled:
         return out
 
 
+def fuse_pairs(prog):
+    """Peephole over the virtual ops: an Fq2 producer whose ONLY consumer is the add-like op that
+    directly follows it becomes one instruction with a post-operation (isa.POST_*): the
+    intermediate is never stored or reloaded and one fetch / decode / dispatch round is saved
+    (a fifth of the pairing program's instructions).  Returns (ops, section marks)."""
+    ops = prog.ops
+    n = len(ops)
+
+    def root(x):
+        return x.parent if isinstance(x, Half) else x
+
+    n_uses = {}
+    for op in ops:
+        operands = (list(op.d) + list(op.a)) if op.name == "XCHG" else (op.a, op.b, op.aux)
+        for x in operands:
+            if _is_val(x):
+                n_uses[root(x).id] = n_uses.get(root(x).id, 0) + 1
+    for v in prog.keep:
+        n_uses[v.id] = n_uses.get(v.id, 0) + 1
+    n_defs = {}
+    for op in ops:
+        if op.name != "XCHG" and _is_val(op.d):
+            n_defs[root(op.d).id] = n_defs.get(root(op.d).id, 0) + 1
+    body0, epi0 = prog.section_marks["body"], prog.section_marks["epilogue"]
+    out, marks = [], {"body": None, "epilogue": None}
+    depth = 0
+    i = 0
+    while i < n:
+        if i == body0:
+            marks["body"] = len(out)
+        if i == epi0:
+            marks["epilogue"] = len(out)
+        op = ops[i]
+        if op.name == "SKIPZ":
+            depth += 1
+        elif op.name == "SKIP_END":
+            depth -= 1
+        nxt = ops[i + 1] if i + 1 < n else None
+        fused = None
+        if (nxt is not None and depth == 0 and op.name in isa.POST_PRIMARY and op.aux is None
+                and isinstance(op.d, V2) and nxt.name in isa.POST_SECONDARY and isinstance(nxt.d, V2)
+                and i + 1 != body0 and i + 1 != epi0
+                and op.d.id not in prog.persistent and n_defs.get(op.d.id, 0) == 1
+                and n_uses.get(op.d.id, 0) == 1):
+            x = op.d
+            if nxt.name == "ADD2" and (nxt.a is x) != (nxt.b is x) and isinstance(nxt.a, V2) and isinstance(nxt.b, V2):
+                fused = (isa.POST_ADD, nxt.b if nxt.a is x else nxt.a)
+            elif nxt.name == "SUB2" and (nxt.a is x) != (nxt.b is x) and isinstance(nxt.a, V2) and isinstance(nxt.b, V2):
+                fused = (isa.POST_SUB, nxt.b) if nxt.a is x else (isa.POST_RSUB, nxt.a)
+            elif nxt.name == "MULXI2" and nxt.a is x:
+                fused = (isa.POST_XI, None)
+            elif nxt.name == "DBL2" and nxt.a is x:
+                fused = (isa.POST_DBL, None)
+        if fused is not None:
+            out.append(VOp(op.name, nxt.d, op.a, op.b, fused[1], post=fused[0]))
+            i += 2
+            continue
+        out.append(op)
+        i += 1
+    if marks["body"] is None:
+        marks["body"] = len(out) if body0 is not None and body0 >= n else 0
+    if epi0 is not None and marks["epilogue"] is None:
+        marks["epilogue"] = len(out)
+    return out, marks
+
+
 def _assemble(prog, n_slots, n_cold, n_smem=None):
     if n_smem is None:
         n_smem = n_slots
-    ops = prog.ops
+    ops, section_marks = fuse_pairs(prog)
     n = len(ops)
     INF = 1 << 60
 
@@ -435,7 +501,7 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
     use_ptr = {k: 0 for k in uses}
     # values that cross the prologue/body boundary (or are persistent variables) keep a fixed
     # cell for the whole program: the body is executed many times with the same assignment
-    body0 = prog.section_marks["body"]
+    body0 = section_marks["body"]
     fixed = set(prog.persistent)
     for vid, lst in uses.items():
         if lst[0] < body0 <= lst[-1] and body0 > 0:
@@ -494,7 +560,7 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
             stats["spills"] += 1
         return s
 
-    epi0 = prog.section_marks["epilogue"]
+    epi0 = section_marks["epilogue"]
     cur_op = [0]
 
     def release(vid):
@@ -512,9 +578,9 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
     region_pins = set()
     for i, op in enumerate(ops):
         cur_op[0] = i
-        if i == prog.section_marks["body"]:
+        if i == section_marks["body"]:
             marks[0] = len(out)
-        if i == prog.section_marks["epilogue"]:
+        if i == section_marks["epilogue"]:
             marks[1] = len(out)
         if op.name == "XCHG":
             if skip_stack:
@@ -600,7 +666,7 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                 held.append(alloc_slot(i, region_pins))
             free_slots.extend(held)
         fields = [op.d, op.a, op.b]
-        srcs = [x for x in (op.a, op.b) if _is_val(x) and not isinstance(root(x), Flag)]
+        srcs = [x for x in (op.a, op.b) + ((op.aux,) if op.post else ()) if _is_val(x) and not isinstance(root(x), Flag)]
         # STBE48/STRAW2/SPILL-like ops read their 'a'; dst-position value operands that are
         # data sources do not exist in this ISA (buffer ids are ints)
         pinned = set(root(x).id for x in srcs)
@@ -637,7 +703,10 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                 conc[k] = int(x)
         aux = 0
         if op.aux is not None:
-            aux = flag_of[op.aux.id] if _is_val(op.aux) else int(op.aux)
+            if op.post:
+                aux = 2 * slot_of[op.aux.id]            # third source cell of a fused instruction
+            else:
+                aux = flag_of[op.aux.id] if _is_val(op.aux) else int(op.aux)
         # free sources that die here (so the destination can reuse their cells), except for
         # cross-thread reads where other threads still read the source after we write
         dying = []
@@ -676,7 +745,7 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
             conc[0] = int(op.d)
         if op.name == "SKIPZ":
             skip_stack.append(len(out))
-        emit(op.name, conc[0], conc[1], conc[2], aux)
+        emit(op.name, conc[0] | (op.post << isa.POST_SHIFT), conc[1], conc[2], aux)
         for vid in dying:
             if vid in flag_of:
                 free_flags.append(flag_of.pop(vid))

@@ -66,6 +66,14 @@ OPCODE = {name: i for i, (name, _, _) in enumerate(OPS)}
 OPNAME = {i: name for name, i in OPCODE.items()}
 OPSIG = {name: sig.split() for name, sig, _ in OPS}
 
+# Post-operations: the hot Fq2 producers can apply one more add-like step to their result z before
+# storing it (builder.fuse_pairs).  Code in bits 12..14 of the destination operand (cells and
+# cold slots are < 4096), third source cell c in aux.
+POST_NONE, POST_ADD, POST_SUB, POST_RSUB, POST_XI, POST_DBL = 0, 1, 2, 3, 4, 5   # z+c, z-c, c-z, xi*z, 2z
+POST_SHIFT = 12
+POST_PRIMARY = ("ADD2", "SUB2", "SQR2", "MUL2", "MULXI2")
+POST_SECONDARY = ("ADD2", "SUB2", "MULXI2", "DBL2")
+
 N_FLAGS = 32
 INS_BYTES = 8
 
@@ -97,4 +105,7 @@ def c_header():
     lines.append("// bit4/5 store the result to d as Fq/Fq2")
     lines.append("enum VmOpInfo : unsigned { VM_A1 = 1, VM_A2 = 2, VM_B1 = 4, VM_B2 = 8, VM_D1 = 16, VM_D2 = 32 };")
     lines.append("#define VM_OP_INFO_TABLE {%s}" % ", ".join(str(op_info(n)) for n, _, _ in OPS))
+    lines.append("// post-operation of the hot Fq2 producers: bits 12..14 of the destination operand, third source in aux")
+    lines.append("enum VmPost : int { POST_NONE = %d, POST_ADD = %d, POST_SUB = %d, POST_RSUB = %d, POST_XI = %d, "
+                 "POST_DBL = %d, POST_SHIFT = %d };" % (POST_NONE, POST_ADD, POST_SUB, POST_RSUB, POST_XI, POST_DBL, POST_SHIFT))
     return "\n".join(lines) + "\n"

@@ -12,7 +12,7 @@ from bls_b200 import _lib, engine                           # noqa: E402
 
 _lib.init(0)
 sm = _lib.lib.b200bls_sm_count()
-n = sm * 128 * 6
+n = sm * 128 * 12
 rng = np.random.default_rng(7)
 P = rng.integers(0, 256, size=(n, 96), dtype=np.uint8)
 Q = rng.integers(0, 256, size=(n, 192), dtype=np.uint8)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small fixed workload for ncu: three launches of the pairing program over one full wave
-(2 CTAs x 128 threads per SM), inputs resident on the device."""
+(default: the wide shape, one 384-thread CTA per SM), inputs resident on the device."""
 import os
 import sys
 
@@ -12,8 +12,9 @@ from bls_b200 import _lib, engine                           # noqa: E402
 
 _lib.init(0)
 if _lib.lib.b200bls_get_ctas_per_sm() == 0:
-    _lib.check(_lib.lib.b200bls_set_ctas_per_sm(3))
-n = _lib.lib.b200bls_sm_count() * 128 * _lib.lib.b200bls_get_ctas_per_sm()
+    _lib.check(_lib.lib.b200bls_set_ctas_per_sm(4))
+shape = _lib.lib.b200bls_get_ctas_per_sm()
+n = _lib.lib.b200bls_sm_count() * 128 * min(shape, 3)      # one full wave (shape 4 = one 384-thread CTA per SM)
 rng = np.random.default_rng(7)
 P = rng.integers(0, 256, size=(n, 96), dtype=np.uint8)
 Q = rng.integers(0, 256, size=(n, 192), dtype=np.uint8)
