@@ -325,36 +325,42 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) vm_kernel(const __grid_constant_
   // batch is exhausted (CTAs that find no work left exit early, so the CTAs of the next launch
   // on another stream can move in: no tail-wave quantisation across back-to-back batches);
   // epilogue once.  One copy of the interpreter loop serves all three sections.
-  if (p.seg_start != nullptr) {
+  // segmented mode: this thread's segment and the longest segment of the CTA
+  const bool seg_mode = p.seg_start != nullptr;
+  unsigned seg_s0 = 0, seg_len = 0, seg_iters = 0, seg_k = 0;
+  if (seg_mode) {
     __shared__ unsigned s_max;
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
-    unsigned s0 = 0, len = 0;
     if (gtid < p.n_items) {
-      s0 = __ldg(p.seg_start + gtid);
-      len = __ldg(p.seg_start + gtid + 1) - s0;
+      seg_s0 = __ldg(p.seg_start + gtid);
+      seg_len = __ldg(p.seg_start + gtid + 1) - seg_s0;
     }
-    const unsigned wmax = __reduce_max_sync(0xffffffffu, len);
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, seg_len);
     if ((threadIdx.x & 31) == 0) atomicMax(&s_max, wmax);
     __syncthreads();
-    const unsigned iters = s_max;  // longest segment of this CTA
-    vm_run_section(env, p.code, 0, p.body_start);
-    for (unsigned k = 0; k < iters; k++) {
-      const bool act = k < len;
-      env.item = act ? (long long)__ldg(p.seg_idx + s0 + k) : 0;
-      env.item_raw = act ? 0 : p.n_items;  // FACTIVE reads item_raw < n_items
-      vm_run_section(env, p.code, p.body_start, p.epi_start);
-    }
-    env.item_raw = gtid;
-    env.item = gtid < last ? gtid : last;
-    vm_run_section(env, p.code, p.epi_start, p.n_ins);
-  } else
+    seg_iters = s_max;
+  }
   for (int phase = 0; phase < 3;) {
     int lo, hi;
     if (phase == 0) {
       lo = 0;
       hi = p.body_start;
       phase = 1;
+    } else if (phase == 1 && seg_mode) {
+      // body iteration k handles the k-th record of this thread's segment
+      if (seg_k >= seg_iters) {
+        phase = 2;
+        env.item_raw = gtid;
+        env.item = gtid < last ? gtid : last;
+        continue;
+      }
+      const bool act = seg_k < seg_len;
+      env.item = act ? (long long)__ldg(p.seg_idx + seg_s0 + seg_k) : 0;
+      env.item_raw = act ? 0 : p.n_items;  // FACTIVE reads item_raw < n_items
+      seg_k++;
+      lo = p.body_start;
+      hi = p.epi_start;
     } else if (phase == 1) {
       // (tried: item blocks of 128 fetched per group of four warps through named barriers -- worse:
       // a wide CTA then stays resident until its slowest group is done and the next launch's CTA
