@@ -295,6 +295,16 @@ def run_gpu(args, rank, world, dist):
     except Exception:
         pass
     cpu_v, cpu_cores, cpu_sample = cpu_pairings_per_second(per_core=3)
+    # DRAM bytes of one launch of the pairing kernel at this batch size: dram__bytes_read.sum +
+    # dram__bytes_write.sum of the committed `ncu --set full` capture (tools/ncu_summary.py)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_pairing_final_ncu.json")) as fh:
+            cap = json.load(fh)
+        if "n = 65,536" in cap["description"] and n == 65536 and lib.b200bls_get_ctas_per_sm() == 4:
+            traffic = cap["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -306,10 +316,11 @@ def run_gpu(args, rank, world, dist):
         "e2e": {"value": e2e, "unit": METRIC, "h2d_bytes_per_step": n * 288, "d2h_bytes_per_step": n * 576,
                 "steps": e2e_steps, "api": "b200bls_pairing_batch_async + b200bls_sync (pinned host buffers, 2 streams)"},
         "roofline": {"bound": "int32_mul", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
-                     "unit": "T limb-products/s", "frac": achieved / peak_ops, "traffic": None,
+                     "unit": "T limb-products/s", "frac": achieved / peak_ops, "traffic": traffic,
                      "note": "achieved = pairings/s/GPU x 15,200 M x 300 limb products (SURVEY 8d); peak = "
                              "IMAD.WIDE.U32.X carry-chain microbenchmark measured in this run; per-launch "
-                             "algorithmic HBM bytes %d (%.4f of measured HBM peak at this rate)"
+                             "algorithmic HBM bytes %d (%.4f of measured HBM peak at this rate); traffic = DRAM bytes of "
+                             "one launch from profiles/r1_pairing_final_ncu.json (workspace spills to the L2-backed cold area)"
                              % (hbm_bytes, (per_gpu * 864 / 1e9) / peaks.get("hbm_gbs", 6553.3))},
         "cpu_baseline": {"value": cpu_v, "unit": METRIC, "cores": cpu_cores, "kind": "port", "sample": cpu_sample},
         "clocks": clocks,

@@ -15,6 +15,7 @@ if _lib.lib.b200bls_get_ctas_per_sm() == 0:
     _lib.check(_lib.lib.b200bls_set_ctas_per_sm(4))
 shape = _lib.lib.b200bls_get_ctas_per_sm()
 n = _lib.lib.b200bls_sm_count() * 128 * min(shape, 3)      # one full wave (shape 4 = one 384-thread CTA per SM)
+n = int(os.environ.get("B200BLS_PROFILE_N", n))            # e.g. 65536 = bench.py's batch
 rng = np.random.default_rng(7)
 P = rng.integers(0, 256, size=(n, 96), dtype=np.uint8)
 Q = rng.integers(0, 256, size=(n, 192), dtype=np.uint8)
