@@ -181,7 +181,7 @@ def run_gpu(args, rank, world, dist):
         p2, q2 = engine.DeviceBuffer(96 * n).upload(hP), engine.DeviceBuffer(192 * n).upload(hQ)
         sets.append((p2, q2, engine.DeviceBuffer(576 * n)))
 
-    N_STREAMS = 2        # consecutive batches go to alternating library streams and overlap
+    N_STREAMS = int(os.environ.get("B200BLS_BENCH_STREAMS", "2"))   # consecutive batches go to alternating library streams and overlap
 
     def step(i):
         p, q, o = sets[i % NSETS]
@@ -314,7 +314,7 @@ def run_gpu(args, rank, world, dist):
                    % (NSETS, NSETS * hbm_bytes // 2 ** 20), "ctas_per_sm": lib.b200bls_get_ctas_per_sm(), "streams": N_STREAMS,
                    "parity_spot_check": parity},
         "e2e": {"value": e2e, "unit": METRIC, "h2d_bytes_per_step": n * 288, "d2h_bytes_per_step": n * 576,
-                "steps": e2e_steps, "api": "b200bls_pairing_batch_async + b200bls_sync (pinned host buffers, 2 streams)"},
+                "steps": e2e_steps, "api": "b200bls_pairing_batch_async + b200bls_sync (pinned host buffers, %d streams)" % N_STREAMS},
         "roofline": {"bound": "int32_mul", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
                      "unit": "T limb-products/s", "frac": achieved / peak_ops, "traffic": traffic,
                      "note": "achieved = pairings/s/GPU x 15,200 M x 300 limb products (SURVEY 8d); peak = "
