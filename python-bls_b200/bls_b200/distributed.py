@@ -65,6 +65,23 @@ def point_sum(points, g2, dist=None):
     return engine.point_sum(b"".join(parts), g2).tobytes()
 
 
+def secure_sum(points, pk_hash, first_index, g2, dist=None):
+    """secure aggregation sum_i T_i * P_i sharded across ranks (bls.py:29-56, 217-221): `points` is
+    THIS rank's contiguous slice starting at global index `first_index`; the exponents
+    T_i = H(i || pk_hash) mod n are computed on the device for exactly that index range, the
+    slice goes through one multi-scalar multiplication, and the per-rank points are gathered
+    and summed like plain partial sums."""
+    from . import engine
+    w = 192 if g2 else 96
+    n = np.asarray(points).size // w if not isinstance(points, (bytes, bytearray)) else len(points) // w
+    ts = engine.hash_pks(pk_hash, n, first=first_index)
+    part = engine.msm(points, ts, g2).tobytes()
+    parts = gather_bytes(part, dist)
+    if len(parts) == 1:
+        return parts[0]
+    return engine.point_sum(b"".join(parts), g2).tobytes()
+
+
 def verify_batch(pks, hashes, sigs, dist=None):
     """independent verifications: every rank checks its own slice, no exchange"""
     from . import engine

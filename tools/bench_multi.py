@@ -81,6 +81,16 @@ import bls_oracle as O                                         # noqa: E402  (ch
 tot = sum(int.from_bytes(bytes(r), "big") for r in synth.scalars(synth.SEED_AGGREGATE, n3)) % O.N
 want = O.aff_mul(tot, O.G2)
 out["config3_parity"] = ref == b"".join(c.to_bytes(48, "big") for c in (want[0][0], want[0][1], want[1][0], want[1][1]))
+# ---- config 3, secure variant: sum T_i * sig_i over the same 1 M points (row f3) -------------------
+import hashlib                                                 # noqa: E402
+pk_hash = hashlib.sha256(b"config 3 secure").digest()
+sec, res = timed(lambda: D.secure_sum(pts, pk_hash, lo, True, Group(None, "nccl")), reps=2)
+ks = [int.from_bytes(bytes(r), "big") for r in synth.scalars(synth.SEED_AGGREGATE, n3)]
+dot = sum(k * (int.from_bytes(hashlib.sha256(i.to_bytes(4, "big") + pk_hash).digest(), "big") % O.N)
+          for i, k in enumerate(ks)) % O.N
+want = O.aff_mul(dot, O.G2)
+out["config3_secure_g2_msm_nccl"] = {"seconds": sec, "points_per_s": n3 / sec,
+                                     "parity": res == b"".join(c.to_bytes(48, "big") for c in (want[0][0], want[0][1], want[1][0], want[1][1]))}
 # ---- config 4 (large): 400,000 messages in total ------------------------------------------------
 n4 = 400_000
 lo, hi = D.shard_range(n4, rank, world)
