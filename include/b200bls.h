@@ -189,6 +189,11 @@ int b200bls_hash_pks_dev(const void* pk_hash32, uint32_t first_index, void* out,
  * pk: n x 96, mh: n x 32, sig: n x 192 (affine), ok: n bytes. */
 int b200bls_verify_batch(const uint8_t* pk, const uint8_t* mh, const uint8_t* sig, uint8_t* ok, size_t n);
 int b200bls_verify_batch_dev(const void* pk, const void* mh, const void* sig, void* ok, size_t n);
+/* The same from the wire formats: pk48 = n x 48-byte PublicKey.serialize() bytes, sig96 = n x 96-byte
+ * Signature.serialize() bytes, decoded on the device (keys.py:29-40, signature.py:22-38).  A key or
+ * signature that does not decode -- the reference raises ValueError -- gives ok[i] = 0. */
+int b200bls_verify_batch_wire(const uint8_t* pk48, const uint8_t* mh, const uint8_t* sig96, uint8_t* ok, size_t n);
+int b200bls_verify_batch_wire_dev(const void* pk48, const void* mh, const void* sig96, void* ok, size_t n);
 /* One aggregate signature over n distinct message hashes (bls.py:194-201):
  * *ok = (e(-G1, sig) * prod_i e(pk_i, H(mh_i)) == 1).  n + 1 Miller loops, one final
  * exponentiation.  pks are the per-message public-key sums the host-side grouping produced. */

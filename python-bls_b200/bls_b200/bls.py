@@ -96,6 +96,14 @@ class BLS:
         return [bool(r) for r in res]
 
     @staticmethod
+    def verify_batch_bytes(public_key_bytes, message_hashes, signature_bytes):
+        """the same from serialised keys (48 B) and signatures (96 B): PublicKey.from_bytes /
+        Signature.from_bytes run on the GPU too; where the reference would raise ValueError while
+        decoding, the result is False"""
+        res = engine.verify_batch_wire(b"".join(public_key_bytes), b"".join(message_hashes), b"".join(signature_bytes))
+        return [bool(r) for r in res]
+
+    @staticmethod
     def aggregate_pub_keys(public_keys, secure):
         """bls.py:204-223 (sorts its argument in place, like the reference)"""
         if len(public_keys) < 1:

@@ -184,6 +184,19 @@ def hash_to_g2(hashes):
     return out
 
 
+def verify_batch_wire(pks48, hashes, sigs96):
+    """n x (serialised pk 48 B, message hash 32 B, serialised sig 96 B) -> n result bytes; inputs that
+    do not decode are rejections"""
+    _lib.init()
+    pks48, hashes, sigs96 = as_u8(pks48), as_u8(hashes), as_u8(sigs96)
+    n = hashes.size // 32
+    if pks48.size != 48 * n or hashes.size != 32 * n or sigs96.size != 96 * n:
+        raise ValueError("bad buffer sizes")
+    out = np.empty(n, dtype=np.uint8)
+    check(lib.b200bls_verify_batch_wire(ptr(pks48), ptr(hashes), ptr(sigs96), ptr(out), n))
+    return out
+
+
 def verify_batch(pks, hashes, sigs):
     """n x (pk 96 B, message hash 32 B, sig 192 B) -> n result bytes"""
     _lib.init()

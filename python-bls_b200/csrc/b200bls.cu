@@ -553,6 +553,38 @@ int verify_dev(const void* pk, const void* mh, const void* sig, void* ok, size_t
   return launch_named("verify_pair", n, b, 4);
 }
 
+__global__ void and3_kernel(uint8_t* __restrict__ ok, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, long long n) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) ok[t] = (ok[t] && a[t] && b[t]) ? 1 : 0;
+}
+
+// verification straight from the wire formats: PublicKey.from_bytes (keys.py:29-40) and
+// Signature.from_bytes (signature.py:22-38) on the device, then the pairing check; a key or
+// signature that does not decode (the reference raises ValueError) counts as a rejection
+int verify_wire_dev(const void* pk48, const void* mh, const void* sig96, void* ok, size_t n) {
+  NEED_READY();
+  if (n == 0) return 0;
+  int rc = ensure_scratch(6, (size_t)96 * n);
+  if (!rc) rc = ensure_scratch(11, (size_t)192 * n);
+  if (!rc) rc = ensure_scratch(7, n);
+  if (!rc) rc = ensure_scratch(8, n);
+  if (rc) return rc;
+  StreamCtx& sc = cur();
+  VmBuf b1[3] = {vb(pk48, 48), vb(sc.scratch[6].ptr, 96), vb(sc.scratch[7].ptr, 1)};
+  rc = launch_named("g1_decompress", n, b1, 3);
+  if (rc) return rc;
+  VmBuf b2[3] = {vb(sig96, 96), vb(sc.scratch[11].ptr, 192), vb(sc.scratch[8].ptr, 1)};
+  rc = launch_named("g2_decompress", n, b2, 3);
+  if (rc) return rc;
+  rc = verify_dev(sc.scratch[6].ptr, mh, sc.scratch[11].ptr, ok, n);
+  if (rc) return rc;
+  and3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((uint8_t*)ok, (const uint8_t*)sc.scratch[7].ptr,
+                                                             (const uint8_t*)sc.scratch[8].ptr, (long long)n);
+  CU(cudaGetLastError());
+  g_ctx.launches++;
+  return 0;
+}
+
 // x bytes of each affine point with (flag << 7) OR-ed into byte 0 (bls_py/ec.py:103-111)
 __global__ void compress_pack_kernel(const uint8_t* __restrict__ aff, const uint8_t* __restrict__ flag,
                                      uint8_t* __restrict__ out, long long n, int xbytes) {
@@ -1083,6 +1115,16 @@ int b200bls_verify_batch_dev(const void* pk, const void* mh, const void* sig, vo
   return verify_dev(pk, mh, sig, ok, n);
 }
 
+int b200bls_verify_batch_wire(const uint8_t* pk48, const uint8_t* mh, const uint8_t* sig96, uint8_t* ok, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!pk48 || !mh || !sig96 || !ok) return fail(B200BLS_E_ARG, "null buffer");
+  HostIO io[4] = {{pk48, nullptr, 48 * n}, {mh, nullptr, 32 * n}, {sig96, nullptr, 96 * n}, {nullptr, ok, n}};
+  return with_staging(io, 4, [&](void** d) { return verify_wire_dev(d[0], d[1], d[2], d[3], n); });
+}
+int b200bls_verify_batch_wire_dev(const void* pk48, const void* mh, const void* sig96, void* ok, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return verify_wire_dev(pk48, mh, sig96, ok, n);
+}
 
 // e(-G1, sig) * prod_i e(pk_i, H(mh_i)) == 1 for distinct message hashes and unit exponents:
 // the core of BLS.verify (bls_py/bls.py:194-201) after its host-side grouping

@@ -138,3 +138,41 @@ def test_batch_verify_with_corruption():
     want = np.ones(n, dtype=np.uint8)
     want[bad] = 0
     assert np.array_equal(res, want)
+
+
+def test_verify_from_wire_bytes():
+    """row f1: verification straight from the serialised formats; a signature or key that does not
+    decode (the reference raises in from_bytes) is a rejection, never an error"""
+    from bls_b200 import BLS, engine
+    g = load_golden("sig_kat.json")
+    tab = g["verify_table"]
+    pks = [bytes.fromhex(t["pk"]) for t in tab]
+    hs = [bytes.fromhex(t["h"]) for t in tab]
+    sigs = [bytes.fromhex(t["sig"]) for t in tab]
+    want = [t["ok"] for t in tab]
+    # byte-level corruption of a valid signature (about half do not decode), same key and message
+    flips = g["bitflips"]
+    for c in flips["cases"]:
+        pks.append(bytes.fromhex(flips["pk"]))
+        hs.append(bytes.fromhex(flips["h"]))
+        sigs.append(bytes.fromhex(c["sig"]))
+        want.append(c["ok"])
+    # corrupted public keys: x values with no point on the curve, and a decodable wrong key
+    bad_pk = None
+    for i in range(1, 60):
+        cand = bytearray(pks[0])
+        cand[20] ^= i
+        try:
+            O.g1_deserialize(bytes(cand))
+        except ValueError:
+            bad_pk = bytes(cand)
+            break
+    assert bad_pk is not None
+    pks += [bad_pk, pks[1]]
+    hs += [hs[0], hs[0]]
+    sigs += [sigs[0], sigs[0]]
+    want += [False, False]
+    assert BLS.verify_batch_bytes(pks, hs, sigs) == want
+    assert any(want) and not all(want)
+    assert sum(1 for c in flips["cases"] if not c["decodes"]) > 0
+    assert engine.verify_batch_wire(b"", b"", b"").size == 0
