@@ -160,17 +160,38 @@ class Curve:
         return self.sel(inf, zero, ax), self.sel(inf, zero, ay)
 
     def scalar_mul(self, x, y, inf, scalar_buf, n_bits=256):
-        """k * (x, y) for the item's 32-byte big-endian scalar: MSB-first double and
-        (mixed) add; bits are per-thread flags, so every lane runs the same code."""
+        """k * (x, y) for the item's 32-byte big-endian scalar: MSB-first, two bits per step.
+        P, 2P and 3P are kept affine (one shared inversion), so a step is two doublings and ONE
+        mixed addition of the entry the two scalar bits select -- per-thread flags and selects, so
+        every lane runs the same code (the reference's ladder, fields_t.py:705-740, adds once per
+        set bit; a uniform one-bit ladder would add once per bit).  Exact for every curve point,
+        small-order ones included: 2P or 3P may be infinity, which the table carries as flags."""
+        assert n_bits % 2 == 0
         prog = self.prog
+        one = self.const(1)
+        p2 = self.double(self.from_affine(x, y, inf))
+        p3 = self.add(p2, (x, y), mixed=True, inf2=inf)
+        inf2p, inf3p = p2[2].is_zero(), p3[2].is_zero()
+        z2 = self.sel(inf2p, one, p2[2])
+        z3 = self.sel(inf3p, one, p3[2])
+        w = self.inv(z2 * z3)
+        zi2, zi3 = w * z3, w * z2
+        zi2s, zi3s = zi2.sqr(), zi3.sqr()
+        x2, y2 = p2[0] * zi2s, p2[1] * (zi2s * zi2)
+        x3, y3 = p3[0] * zi3s, p3[1] * (zi3s * zi3)
         acc = self.infinity()
-        acc = (acc[0], acc[1], acc[2])
-        for bit in range(n_bits - 1, -1, -1):
-            if bit != n_bits - 1:
-                acc = self.double(acc)
-            f = prog.flag_bit(scalar_buf, bit)
-            s = self.add(acc, (x, y), mixed=True, inf2=inf)
-            acc = tuple(self.sel(f, a, b) for a, b in zip(s, acc))
+        for bit in range(n_bits - 2, -2, -2):
+            if bit != n_bits - 2:
+                acc = self.double(self.double(acc))
+            d1 = prog.flag_bit(scalar_buf, bit + 1)
+            d0 = prog.flag_bit(scalar_buf, bit)
+            tx = self.sel(d1, self.sel(d0, x3, x2), x)
+            ty = self.sel(d1, self.sel(d0, y3, y2), y)
+            # infinity flag of the selected entry: d1 ? (d0 ? inf3p : inf2p) : inf
+            tinf = (d1 & ((d0 & inf3p) | (~d0 & inf2p))) | (~d1 & inf)
+            s = self.add(acc, (tx, ty), mixed=True, inf2=tinf)
+            nz = d1 | d0
+            acc = tuple(self.sel(nz, a, b) for a, b in zip(s, acc))
         return acc
 
 

@@ -42,6 +42,40 @@ def test_scalar_edge_values():
     assert engine.scalar_mul(bytes(96), (5).to_bytes(32, "big"), False).tobytes() == bytes(96)
 
 
+def test_scalar_mul_small_order_and_off_subgroup_points():
+    """the windowed ladder keeps P, 2P, 3P in a table: (0, 2) has order 3 on E(Fq) (3P is infinity,
+    2P = -P), so every table entry and the infinity bookkeeping is exercised; off-subgroup points
+    (decoded from arbitrary x) must behave like any other point"""
+    from bls_b200 import engine
+    p3 = (0, 2, False)
+    assert O.aff_mul(3, p3)[2] and not O.aff_mul(2, p3)[2]
+    ks = list(range(0, 14)) + [O.N - 1, O.N, (1 << 256) - 1, 0x5555555555555555 << 190, 0xaaaaaaaa << 224 | 0xffff]
+    sc = b"".join(k.to_bytes(32, "big") for k in ks)
+    out = engine.scalar_mul(ser1(p3) * len(ks), sc, False).tobytes()
+    for i, k in enumerate(ks):
+        want = O.aff_mul(k % 3, p3)
+        assert out[96 * i:96 * (i + 1)] == (bytes(96) if want[2] else ser1(want)), k
+    # off-subgroup points on both curves
+    rng = np.random.default_rng(17)
+    for g2 in (False, True):
+        w = 192 if g2 else 96
+        pts = []
+        x = 5
+        while len(pts) < 3:
+            x += 1
+            try:
+                cand = (O.g2_y_for_x((x, 1)) if g2 else O.g1_y_for_x(x))
+            except ValueError:
+                continue
+            pts.append(((x, 1), cand[0], False) if g2 else (x, cand[0], False))
+        ks = [int.from_bytes(rng.bytes(32), "big") for _ in pts]
+        ser = ser2 if g2 else ser1
+        out = engine.scalar_mul(b"".join(ser(p) for p in pts), b"".join(k.to_bytes(32, "big") for k in ks), g2).tobytes()
+        for i, (p, k) in enumerate(zip(pts, ks)):
+            want = O.to_aff(O.jac_mul(k, O.to_jac(p)))
+            assert out[w * i:w * (i + 1)] == (bytes(w) if want[2] else ser(want)), (g2, i)
+
+
 @pytest.mark.parametrize("ctas", [1, 2, 3])
 def test_ragged_batches_every_shape(ctas):
     """batch sizes around the CTA (128) and wave boundaries, one known pairing repeated"""

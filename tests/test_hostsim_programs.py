@@ -181,3 +181,35 @@ def test_host_simulation_detects_cross_thread_hazards():
     assert ok.returncode == 0 and "finished" in ok.stdout, ok.stderr[-500:]
     bad = subprocess.run([sys.executable, "-c", code, "inject"], capture_output=True, text=True)
     assert bad.returncode != 0 and "finished" not in bad.stdout
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_windowed_scalar_mul_program(g2):
+    """the two-bit-window ladder (programs/curve.py: scalar_mul) on the host build of the device
+    code: generator, the order-3 point (0, 2) of E(Fq) (3P = infinity, 2P = -P), infinity, and
+    scalars whose two-bit digits cover 0..3 in every position class"""
+    G = O.G2 if g2 else O.G1
+    w = 192 if g2 else 96
+
+    def ser(p):
+        if p[2]:
+            return bytes(w)
+        if g2:
+            return b"".join(c.to_bytes(48, "big") for c in (p[0][0], p[0][1], p[1][0], p[1][1]))
+        return p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+
+    pts = [G, G, G, G, (G[0], G[1], True)]
+    ks = [0, 1, 0x1b, (0xe4 << 248) | 0x93, 12345]
+    if not g2:
+        pts += [(0, 2, False)] * 4
+        ks += [1, 2, 3, 0x7d]
+    asm = curve.build_scalar_mul(g2)().assemble(18, n_cold=4096, n_tmem=21)
+    P = np.frombuffer(b"".join(ser((p[0], p[1], p[2] if len(p) > 2 else False)) for p in pts), dtype=np.uint8).copy()
+    S = np.frombuffer(b"".join(k.to_bytes(32, "big") for k in ks), dtype=np.uint8).copy()
+    out = np.zeros(w * len(pts), dtype=np.uint8)
+    hostsim.run(asm, {0: P, 1: S, 2: out}, {0: w, 1: 32, 2: w}, len(pts), n_blocks=3, nt=3)
+    raw = out.tobytes()
+    for i, (p, k) in enumerate(zip(pts, ks)):
+        base = (p[0], p[1], p[2] if len(p) > 2 else False)
+        want = O.to_aff(O.jac_mul(k, O.to_jac(base))) if not base[2] else (0, 0, True)
+        assert raw[w * i:w * (i + 1)] == ser(want), (g2, i, k)
