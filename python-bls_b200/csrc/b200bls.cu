@@ -360,18 +360,15 @@ __global__ void msm_count_kernel(const uint8_t* __restrict__ scalars, unsigned* 
 //                2-bit top window of a 255-bit scalar -- must not serialise the fold)
 // Clears count so that the scatter pass can reuse it as the per-bucket cursor.
 __global__ void __launch_bounds__(1024) msm_scan_kernel(unsigned* __restrict__ count, unsigned* __restrict__ start,
-                                unsigned* __restrict__ seg_first, unsigned seg_len) {
+                                                        unsigned* __restrict__ seg_first, unsigned seg_len) {
   constexpr int PER = MSM_B / 1024;
   __shared__ unsigned part[1024], part2[1024];
   const int t = threadIdx.x;
-  unsigned local[PER];
   unsigned sum = 0, sum2 = 0;
-#pragma unroll
   for (int k = 0; k < PER; k++) {
-    local[k] = count[t * PER + k];
-    sum += local[k];
-    sum2 += (local[k] + seg_len - 1) / seg_len;
-    count[t * PER + k] = 0;
+    const unsigned c = count[t * PER + k];
+    sum += c;
+    sum2 += (c + seg_len - 1) / seg_len;
   }
   part[t] = sum;
   part2[t] = sum2;
@@ -384,12 +381,13 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(unsigned* __restrict__ c
     __syncthreads();
   }
   unsigned run = part[t] - sum, run2 = part2[t] - sum2;
-#pragma unroll
   for (int k = 0; k < PER; k++) {
+    const unsigned c = count[t * PER + k];   // second pass over this thread's 48 counts (L1 resident)
+    count[t * PER + k] = 0;
     start[t * PER + k] = run;
     seg_first[t * PER + k] = run2;
-    run += local[k];
-    run2 += (local[k] + seg_len - 1) / seg_len;
+    run += c;
+    run2 += (c + seg_len - 1) / seg_len;
   }
   if (t == 1023) {
     start[MSM_B] = run;
