@@ -80,7 +80,8 @@ uint64_t b200bls_launch_count(void);
 
 /* Integer-multiply roofline microbenchmark.  variant 0: IMAD (mad.lo),
  * 1: IMAD.HI, 2: IMAD.WIDE.U32, 3: IMAD.WIDE.U32.X carry chains as in the Montgomery
- * product.  Launches blocks_per_sm x SMs CTAs of `threads` threads (<= 256); reports
+ * product, 4: DFMA (FP64 pipe), 5: even warps variant 3 and odd warps variant 4 (do the two pipes
+ * overlap?).  Launches blocks_per_sm x SMs CTAs of `threads` threads (<= 256); reports
  * multiply-add instructions per second (best of 4 timed launches, CUDA events). */
 int b200bls_microbench_imad(int variant, int blocks_per_sm, int threads, int iters,
                             double* ops_per_second, float* ms_out);

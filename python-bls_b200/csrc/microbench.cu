@@ -7,6 +7,10 @@
 //   variant 2: IMAD.WIDE (mad.wide.u32)         -> 32x32+64 limb products / s
 //   variant 3: IMAD.WIDE.U32.X carry chains (mad.lo.cc/madc.hi.cc pairs, the instruction
 //              mix of fp_mul)                  -> limb products / s
+//   variant 4: DFMA (fma.rn.f64), 8 independent chains -> FP64 FMAs / s (the FP64 pipe is separate
+//              from the integer-multiply pipe: a candidate second multiplier for 52-bit limbs)
+//   variant 5: even warps run variant 3, odd warps variant 4, same instruction count each ->
+//              total instructions / s; tells whether the two pipes overlap
 // "limb-product peak" = max(variant2, variant3, min(variant0, variant1)/2).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,8 +22,30 @@ namespace {
 constexpr int CHAINS = 8;
 constexpr int INNER = 64;
 
+__device__ __forceinline__ uint32_t dfma_body(int iters, uint32_t seed) {
+  double x[CHAINS];
+  const double m = 1.0 + (double)(seed & 7) * 1e-9, c = 1e-3;
+#pragma unroll
+  for (int k = 0; k < CHAINS; k++) x[k] = 1.0 + k * 1e-3 + threadIdx.x * 1e-6;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < INNER; k++) {
+#pragma unroll
+      for (int ch = 0; ch < CHAINS; ch++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[ch]) : "d"(m), "d"(c));
+    }
+  }
+  double r = 0;
+#pragma unroll
+  for (int k = 0; k < CHAINS; k++) r += x[k];
+  return (uint32_t)__double2int_rn(r * 1e-6);
+}
+
 template <int VARIANT>
 __global__ void __launch_bounds__(256) imad_kernel(uint32_t* out, int iters, uint32_t seed) {
+  if (VARIANT == 4 || (VARIANT == 5 && ((threadIdx.x >> 5) & 1))) {
+    out[blockIdx.x * blockDim.x + threadIdx.x] = dfma_body(iters, seed);
+    return;
+  }
   uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
   uint32_t lo[CHAINS], hi[CHAINS];
 #pragma unroll
@@ -85,6 +111,8 @@ extern "C" int b200bls_microbench_imad(int variant, int blocks_per_sm, int threa
       case 0: imad_kernel<0><<<blocks, threads>>>(out, iters, 12345u + rep); break;
       case 1: imad_kernel<1><<<blocks, threads>>>(out, iters, 12345u + rep); break;
       case 2: imad_kernel<2><<<blocks, threads>>>(out, iters, 12345u + rep); break;
+      case 4: imad_kernel<4><<<blocks, threads>>>(out, iters, 12345u + rep); break;
+      case 5: imad_kernel<5><<<blocks, threads>>>(out, iters, 12345u + rep); break;
       default: imad_kernel<3><<<blocks, threads>>>(out, iters, 12345u + rep); break;
     }
     cudaEventRecord(e1);
