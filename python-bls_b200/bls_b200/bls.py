@@ -22,6 +22,7 @@ class BLS:
         """sum of T_i * sig_i in (message hash, pk) order (bls.py:29-56)"""
         if not (len(signatures) == len(public_keys) == len(message_hashes)):
             raise Exception("Invalid number of keys")
+        ec.serialize_many([pk.value for pk in public_keys] + [s.value for s in signatures])
         order = sorted(range(len(signatures)), key=lambda i: (message_hashes[i], public_keys[i], signatures[i]))
         ts = hash_pks_bytes(len(public_keys), public_keys)
         return Signature.from_g2(ec.weighted_sum([signatures[i].value for i in order], ts, True))
@@ -30,6 +31,8 @@ class BLS:
     def aggregate_sigs(signatures):
         """simple aggregation for groups with disjoint messages, secure (exponentiated) for the
         groups that share one (bls.py:59-151)"""
+        ec.serialize_many([pk.value for sig in signatures if sig.aggregation_info is not None
+                           for pk in sig.aggregation_info.public_keys])
         infos = []
         for sig in signatures:
             if sig.aggregation_info is None or sig.aggregation_info.empty():
@@ -60,6 +63,7 @@ class BLS:
         """bls.py:154-201: group keys by message, raise each to its exponent from the
         aggregation tree, one multi-pairing against the hashed messages"""
         info = signature.aggregation_info
+        ec.serialize_many([pk.value for pk in info.public_keys])
         groups = {}
         for mh, pk in zip(info.message_hashes, info.public_keys):
             groups.setdefault(mh, []).append(pk)
@@ -108,6 +112,7 @@ class BLS:
         """bls.py:204-223 (sorts its argument in place, like the reference)"""
         if len(public_keys) < 1:
             raise Exception("Invalid number of keys")
+        ec.serialize_many([pk.value for pk in public_keys])
         public_keys.sort()
         pts = [pk.value for pk in public_keys]
         if secure:
@@ -123,6 +128,7 @@ class BLS:
             raise Exception("Must include public keys in secure aggregation")
         if len(private_keys) != len(public_keys):
             raise Exception("Invalid number of keys")
+        ec.serialize_many([pk.value for pk in public_keys])
         pairs = sorted(zip(public_keys, private_keys), key=lambda t: (t[0], t[1]))
         ts = hash_pks(len(private_keys), public_keys)
         return PrivateKey(sum(sk.value * t for (_, sk), t in zip(pairs, ts)) % GROUP_ORDER)

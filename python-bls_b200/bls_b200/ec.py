@@ -123,7 +123,44 @@ def point_from_bytes(data, g2):
     out, ok = engine.decompress(data, g2)
     if not ok[0]:
         raise ValueError("No y for point x")
-    return Point(out.tobytes(), g2)
+    p = Point(out.tobytes(), g2)
+    p._ser = bytes([data[0] & 0x9f]) + bytes(data[1:])   # what serialize() gives back (spare bits masked)
+    return p
+
+
+def points_from_bytes(buffers, g2):
+    """many PublicKey.from_bytes / Signature.from_bytes decodings in ONE GPU call (row f2: the
+    reference decodes, and later re-serialises, one key at a time).  The serialised form of each
+    point is known at once -- the input with its two spare flag bits cleared (the reference masks
+    them on input and never sets them on output) -- so sorting / hashing these points later costs
+    no further GPU work.  Raises ValueError if any buffer does not decode, like the reference."""
+    buffers = [bytes(b) for b in buffers]
+    if not buffers:
+        return []
+    w = 192 if g2 else 96
+    out, ok = engine.decompress(b"".join(buffers), g2)
+    if not ok.all():
+        raise ValueError("No y for point x (buffer %d)" % int(np.argmin(ok)))
+    raw = out.tobytes()
+    pts = []
+    for i, b in enumerate(buffers):
+        p = Point(raw[w * i:w * (i + 1)], g2)
+        p._ser = bytes([b[0] & 0x9f]) + b[1:]
+        pts.append(p)
+    return pts
+
+
+def serialize_many(points):
+    """fill the serialisation caches of many points with one batched GPU call per group, so
+    that the sorts, sets and dictionaries of the scheme layer (which compare keys by their
+    serialised bytes, keys.py:57-64 in the reference) do no per-key GPU work"""
+    for g2 in (False, True):
+        todo = [p for p in points if p.g2 == g2 and p._ser is None]
+        if len(todo) > 1:
+            w = 96 if g2 else 48
+            ser = engine.compress(b"".join(p.raw for p in todo), g2).tobytes()
+            for i, p in enumerate(todo):
+                p._ser = ser[w * i:w * (i + 1)]
 
 
 def hash_to_point_prehashed_Fq2(h):

@@ -18,6 +18,11 @@ class PublicKey:
         return PublicKey(ec.point_from_bytes(bytes(buffer), False))
 
     @staticmethod
+    def from_bytes_batch(buffers):
+        """many keys decoded in one GPU call; their serialised forms are cached"""
+        return [PublicKey(p) for p in ec.points_from_bytes(buffers, False)]
+
+    @staticmethod
     def from_g1(g1_el):
         assert isinstance(g1_el, ec.Point) and not g1_el.g2
         return PublicKey(g1_el)

@@ -15,6 +15,11 @@ class Signature:
         return Signature(ec.point_from_bytes(bytes(buffer), True), aggregation_info)
 
     @staticmethod
+    def from_bytes_batch(buffers):
+        """many signatures decoded in one GPU call (no aggregation info attached)"""
+        return [Signature(p) for p in ec.points_from_bytes(buffers, True)]
+
+    @staticmethod
     def from_g2(g2_el, aggregation_info=None):
         return Signature(g2_el, aggregation_info)
 

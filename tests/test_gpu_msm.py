@@ -117,3 +117,48 @@ def test_secure_aggregation_reference_vectors():
     g = load_golden("agg_kat.json")["secure_pk_agg"]
     pks = [PublicKey.from_bytes(bytes.fromhex(p)) for p in g["pks"]]
     assert BLS.aggregate_pub_keys(pks, True).serialize().hex() == g["out"]
+
+
+def test_many_keys_through_the_scheme_layer_in_few_launches():
+    """row f2: 3,000 public keys decoded in one call, then aggregated securely (sort by serialised
+    bytes, exponents, multi-scalar multiplication) -- a handful of kernel launches, not one per key,
+    and the same point as the identity sum_i T_i k_i G"""
+    from bls_b200 import BLS, PublicKey, engine, synth
+    from bls_b200._lib import lib
+    from bls_b200.util import hash_pks
+    n = 3000
+    ksc = synth.scalars(4242, n)
+    base = np.frombuffer(ser1(O.G1), dtype=np.uint8)
+    aff = engine.scalar_mul(np.tile(base, n), ksc, False)
+    comp = engine.compress(aff, False).tobytes()
+    bufs = [comp[48 * i:48 * (i + 1)] for i in range(n)]
+    l0 = lib.b200bls_launch_count()
+    pks = PublicKey.from_bytes_batch(bufs)
+    assert [pk.serialize() for pk in pks[:50]] == bufs[:50]
+    agg = BLS.aggregate_pub_keys(list(pks), True)
+    launches = lib.b200bls_launch_count() - l0
+    assert launches < 40, launches
+    order = sorted(range(n), key=lambda i: bufs[i])
+    ts = hash_pks(n, [bufs[i] for i in order])
+    ks = [int.from_bytes(bytes(ksc[i]), "big") for i in order]
+    want = O.aff_mul(sum(t * k for t, k in zip(ts, ks)) % N, O.G1)
+    assert agg.value.raw == ser1(want)
+    # a buffer that does not decode makes the batch raise, like the reference's from_bytes
+    bad = None
+    for i in range(1, 60):
+        cand = bytearray(bufs[0])
+        cand[17] ^= i
+        try:
+            O.g1_deserialize(bytes(cand))
+        except ValueError:
+            bad = bytes(cand)
+            break
+    with pytest.raises(ValueError):
+        PublicKey.from_bytes_batch(bufs[:3] + [bad])
+    # points created on the device get their serialisations in one batched call as well
+    from bls_b200 import ec
+    pts = [ec.Point(aff[96 * i:96 * (i + 1)].tobytes(), False) for i in range(200)]
+    l0 = lib.b200bls_launch_count()
+    ec.serialize_many(pts)
+    assert lib.b200bls_launch_count() - l0 <= 3
+    assert [p.serialize() for p in pts] == bufs[:200]
