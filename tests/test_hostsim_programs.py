@@ -213,3 +213,71 @@ def test_windowed_scalar_mul_program(g2):
         base = (p[0], p[1], p[2] if len(p) > 2 else False)
         want = O.to_aff(O.jac_mul(k, O.to_jac(base))) if not base[2] else (0, 0, True)
         assert raw[w * i:w * (i + 1)] == ser(want), (g2, i, k)
+
+
+def test_instruction_fusion_patterns():
+    """builder.fuse_pairs: every post-operation (z+c, z-c, c-z, xi*z, 2z) behind every primary, on the
+    host build of the device code against plain modular arithmetic; and the cases that must NOT fuse
+    (intermediate used twice, persistent destination, producer and consumer in different sections)"""
+    from bls_b200.vm import isa
+    from bls_b200.vm.builder import Program, fuse_pairs
+
+    def f2(a, b, op):
+        if op == "mul":
+            return ((a[0] * b[0] - a[1] * b[1]) % O.Q, (a[0] * b[1] + a[1] * b[0]) % O.Q)
+        if op == "add":
+            return ((a[0] + b[0]) % O.Q, (a[1] + b[1]) % O.Q)
+        if op == "sub":
+            return ((a[0] - b[0]) % O.Q, (a[1] - b[1]) % O.Q)
+        raise ValueError(op)
+
+    xi = lambda a: ((a[0] - a[1]) % O.Q, (a[0] + a[1]) % O.Q)
+    prog = Program("fusion")
+    prog.begin_body()
+    x = prog.load2_be48(0, 0)
+    y = prog.load2_be48(0, 96)
+    c = prog.load2_be48(0, 192)
+    outs = [
+        (x * y) - c, c - (x * y), (x * y) + c, (x * y).mul_xi(), (x * y).dbl(),
+        x.sqr() - c, c - x.sqr(), x.sqr() + c, x.sqr().mul_xi(), x.sqr().dbl(),
+        x.mul_xi() + c, (x - y) + c, (x - y).mul_xi(), (x + y) - c, c - (x + y), x.mul_xi() - c,
+    ]
+    t = x * y                       # used twice: must stay a separate instruction
+    outs += [t + c, t - c]
+    for k, v in enumerate(outs):
+        prog.store2_be48(1, 96 * k, v)
+    ops, _ = fuse_pairs(prog)
+    n_post = sum(1 for o in ops if o.post)
+    assert n_post == 16, n_post
+    assert sum(1 for o in ops if o.name == "MUL2") == 6 and sum(1 for o in ops if o.name == "MUL2" and o.post) == 5
+    rng = np.random.default_rng(99)
+    vals = [tuple(int.from_bytes(rng.bytes(48), "big") % O.Q for _ in range(2)) for _ in range(3)]
+    vals[2] = (O.Q - 1, 0)          # an edge operand
+    X, Y, C = vals
+    xy, xx = f2(X, Y, "mul"), f2(X, X, "mul")
+    dbl = lambda a: f2(a, a, "add")
+    want = [f2(xy, C, "sub"), f2(C, xy, "sub"), f2(xy, C, "add"), xi(xy), dbl(xy),
+            f2(xx, C, "sub"), f2(C, xx, "sub"), f2(xx, C, "add"), xi(xx), dbl(xx),
+            f2(xi(X), C, "add"), f2(f2(X, Y, "sub"), C, "add"), xi(f2(X, Y, "sub")), f2(f2(X, Y, "add"), C, "sub"),
+            f2(C, f2(X, Y, "add"), "sub"), f2(xi(X), C, "sub"), f2(xy, C, "add"), f2(xy, C, "sub")]
+    inp = np.frombuffer(b"".join(v.to_bytes(48, "big") for p in (X, Y, C) for v in p), dtype=np.uint8).copy()
+    for shape in ((18, 21), (6, 7), (4, 2)):
+        asm = prog.assemble(shape[0], n_cold=4096, n_tmem=shape[1])
+        out = np.zeros(96 * len(outs), dtype=np.uint8)
+        hostsim.run(asm, {0: np.tile(inp, 3), 1: np.tile(out, 3)}, {0: 288, 1: 96 * len(outs)}, 3, n_blocks=1, nt=3)
+        got = hostsim.run(asm, {0: inp, 1: out}, {0: 288, 1: 96 * len(outs)}, 1, n_blocks=1, nt=1)[1].tobytes()
+        for k, w in enumerate(want):
+            assert got[96 * k:96 * (k + 1)] == w[0].to_bytes(48, "big") + w[1].to_bytes(48, "big"), (shape, k)
+    # no fusion across a section boundary or into / out of a persistent variable
+    prog2 = Program("nofuse")
+    acc = prog2.var2(prog2.const2((0, 0)))
+    prog2.begin_body()
+    a = prog2.load2_be48(0, 0)
+    s = a.sqr()
+    prog2.assign(acc, acc + s)      # acc + s: ADD2 producer feeds a MOV2 (not add-like); nothing to fuse with s? (s feeds ADD2)
+    prog2.begin_epilogue()
+    prog2.store2_be48(1, 0, acc.dbl())
+    ops2, marks2 = fuse_pairs(prog2)
+    assert all(o.d is not acc or not o.post for o in ops2)
+    assert marks2["body"] is not None and marks2["epilogue"] is not None
+    assert ops2[marks2["epilogue"]].name in ("DBL2", "STBE48")
