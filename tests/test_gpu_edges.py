@@ -76,17 +76,18 @@ def test_scalar_mul_small_order_and_off_subgroup_points():
             assert out[w * i:w * (i + 1)] == (bytes(w) if want[2] else ser(want)), (g2, i)
 
 
-@pytest.mark.parametrize("ctas", [1, 2, 3])
+@pytest.mark.parametrize("ctas", [1, 2, 3, 4])
 def test_ragged_batches_every_shape(ctas):
-    """batch sizes around the CTA (128) and wave boundaries, one known pairing repeated"""
+    """batch sizes around the CTA (128, or 384 for the wide shape 4) and wave boundaries, one known
+    pairing repeated"""
     from bls_b200 import _lib, engine
     _lib.init()
     _lib.check(_lib.lib.b200bls_set_ctas_per_sm(ctas))
     try:
         p, q = O.aff_mul(9, O.G1), O.aff_mul(4, O.G2)
         want = O.f12_serialize(O.ate_pairing(p, q))
-        wave = _lib.lib.b200bls_sm_count() * 128 * ctas
-        for n in (1, 127, 129, wave - 1, wave + 1):
+        wave = _lib.lib.b200bls_sm_count() * 128 * min(ctas, 3)
+        for n in (1, 127, 129, 383, 385, wave - 1, wave + 1):
             out = engine.pairing_batch(ser1(p) * n, ser2(q) * n).tobytes()
             assert out[:576] == want and out[-576:] == want
             assert out == want * n
@@ -112,3 +113,39 @@ def test_streams_overlap_and_stay_independent():
     want = O.f12_serialize(O.ate_pairing(p, q)) * n
     for o in outs:
         assert o.download().tobytes() == want
+
+
+def test_every_launch_shape_gives_the_same_bytes():
+    """each shape runs differently assembled programs (workspace size, spills, Tensor-Memory use, CTA
+    width): hash-to-G2, scalar multiplication, Miller loop + final exponentiation, verification and
+    decompression must produce identical bytes under all of them"""
+    from bls_b200 import _lib, engine, synth
+    _lib.init()
+    n = 517
+    hs = synth.message_hashes(31, n)
+    sc = synth.scalars(32, n)
+    g1 = np.frombuffer(ser1(O.G1), dtype=np.uint8)
+    results = []
+    try:
+        for ctas in (1, 2, 3, 4):
+            _lib.check(_lib.lib.b200bls_set_ctas_per_sm(ctas))
+            H = engine.hash_to_g2(hs)
+            sig = engine.scalar_mul(H, sc, True)
+            pk = engine.scalar_mul(np.tile(g1, n), sc, False)
+            sig_bad = sig.copy().reshape(n, 192)
+            sig_bad[5], sig_bad[100] = sig_bad[6].copy(), sig_bad[101].copy()
+            ok = engine.verify_batch(pk, hs, sig_bad.reshape(-1))
+            e = engine.pairing_batch(pk[:96 * 40], H[:192 * 40])
+            fe = engine.final_exp_batch(engine.miller_loop_batch(pk[:96 * 40], H[:192 * 40]))
+            comp = engine.compress(sig, True)
+            back, dok = engine.decompress(comp, True)
+            results.append((H.tobytes(), sig.tobytes(), pk.tobytes(), ok.tobytes(), e.tobytes(), fe.tobytes(),
+                            comp.tobytes(), back.tobytes(), dok.tobytes()))
+    finally:
+        _lib.check(_lib.lib.b200bls_set_ctas_per_sm(0))
+    for r in results[1:]:
+        assert r == results[0]
+    ok = np.frombuffer(results[0][3], dtype=np.uint8)
+    assert ok.sum() == n - 2 and ok[5] == 0 and ok[100] == 0
+    assert results[0][4] == results[0][5]                       # pairing == final_exp(miller_loop)
+    assert results[0][7] == results[0][1] and all(results[0][8])
