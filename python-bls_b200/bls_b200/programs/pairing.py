@@ -41,7 +41,7 @@ def double_step(prog, r, xp, yp):
     c = z.sqr()
     e = _mul12_xi(prog, c)              # 3 b' Z^2
     f = e.dbl() + e                     # 9 b' Z^2
-    h = (y * z).dbl()                   # 2 Y Z
+    h = (y + z).sqr() - b - c           # 2 Y Z as (Y + Z)^2 - Y^2 - Z^2: a squaring (2 M) instead of a product (3 M)
     xx = x.sqr()
     l0 = b - e                          # Y^2 - 3 b' Z^2
     l1 = -((xx.dbl() + xx) * xp)        # -3 X^2 xP
