@@ -36,9 +36,10 @@ def to_bytes(value, unit):
     return float(value) * scale
 
 
-def main(rep, out, desc):
+def main(rep, out, desc, index=0):
+    """index: which captured launch of the report (0 = first)"""
     rows = list(csv.reader(io.StringIO(ncu(rep, "raw"))))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + index]
     m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
     lines = [desc, "kernel: %s" % m["Kernel Name"][0], ""]
     for k in KEEP:
@@ -50,7 +51,11 @@ def main(rep, out, desc):
     traffic = to_bytes(*m["dram__bytes_read.sum"]) + to_bytes(*m["dram__bytes_write.sum"])
     # warp stall samples by SASS opcode class
     src = list(csv.reader(io.StringIO(ncu(rep, "source"))))
-    shdr, data = src[1], src[2:]
+    # one block per captured launch: a "Kernel Name" row, a header row, then the instructions
+    starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"]
+    lo = starts[index]
+    hi = starts[index + 1] if index + 1 < len(starts) else len(src)
+    shdr, data = src[lo + 1], [r for r in src[lo + 2:hi] if len(r) == len(src[lo + 1])]
     ix = {h: i for i, h in enumerate(shdr)}
     S, E = ix["# Samples"], ix["Instructions Executed"]
     tot = sum(int(r[S]) for r in data) or 1
@@ -81,4 +86,4 @@ def main(rep, out, desc):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "", int(sys.argv[4]) if len(sys.argv) > 4 else 0)
