@@ -358,7 +358,7 @@ def build_decompress(g2):
         if g2:
             x = prog.load2_be48(0, 0, mask_top=True)
             u, n, cc, ok = _candidate(prog, x)
-            y = _sqrt_selected(prog, u, n, cc)
+            y = _sqrt_selected(prog, u, cc * n)
             flip = y.c1.gt_half() ^ big              # want (y.c1 > q//2) == big
             y = prog.sel2(flip, -y, y)
             zero = prog.const2((0, 0))

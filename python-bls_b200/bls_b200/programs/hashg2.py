@@ -75,9 +75,9 @@ def _candidate(prog, x):
     return u, n, c, ok
 
 
-def _sqrt_selected(prog, u, n, c):
-    """a square root of u in Fq2 given c = n^((q-3)/4), n = norm(u) a nonzero square"""
-    alpha = c * n                                      # sqrt(norm)
+def _sqrt_selected(prog, u, alpha):
+    """a square root of u in Fq2 given alpha with alpha^2 = norm(u) (either sign: exactly one of
+    (u0 + alpha) / 2 and (u0 - alpha) / 2 is a square, and both branches below only use alpha^2)"""
     half = prog.const1(HALF)
     delta = (u.c0 + alpha) * half
     c1 = _root_pow(prog, delta)
@@ -88,6 +88,73 @@ def _sqrt_selected(prog, u, n, c):
     y0 = prog.sel1(is_sq, s, -hlf)
     y1 = prog.sel1(is_sq, hlf, s)
     return prog.pack(y0, y1)
+
+
+# g(x1) g(x2) g(x3) = S^2 with S = (b + 1) P(t^2) / (3 sqrt(-3) t^3 w0^3), P of degree 6 (identity of the
+# Shallue-van de Woestijne map for y^2 = x^3 + b, checked symbolically and, below, numerically).
+# Hence norm(g(x3)) = (N(S) / sqrt(n1 n2))^2 and, when neither g(x1) nor g(x2) is a square,
+# 1 / sqrt(n1 n2) = c1 c2 for c_i = n_i^((q-3)/4): the third candidate needs no exponentiation.
+def _f2i(a, b2):
+    return ((a[0] * b2[0] - a[1] * b2[1]) % Q, (a[0] * b2[1] + a[1] * b2[0]) % Q)
+
+
+def _f2_poly_int(coeffs, x):
+    acc = (0, 0)
+    for c in coeffs:
+        acc = _f2i(acc, x)
+        acc = ((acc[0] + c[0]) % Q, (acc[1] + c[1]) % Q)
+    return acc
+
+
+def _sw_product_coeffs():
+    b = B2
+    pw = [(1, 0)]
+    for _ in range(6):
+        pw.append(_f2i(pw[-1], b))
+
+    def comb(*terms):                    # sum of k * b^e
+        r0 = r1 = 0
+        for k, e in terms:
+            r0 += k * pw[e][0]
+            r1 += k * pw[e][1]
+        return (r0 % Q, r1 % Q)
+
+    return [comb((1, 0)),
+            comb((6, 1), (-3, 0)),
+            comb((15, 2), (-6, 1), (6, 0)),
+            comb((20, 3), (6, 2), (-21, 1), (-7, 0)),
+            comb((15, 4), (24, 3), (9, 2), (6, 1), (6, 0)),
+            comb((6, 5), (21, 4), (24, 3), (6, 2), (-6, 1), (-3, 0)),
+            comb((1, 6), (6, 5), (15, 4), (20, 3), (15, 2), (6, 1), (1, 0))]
+
+
+SW_P = _sw_product_coeffs()              # P(T) = sum SW_P[k] T^(6-k), T = t^2
+# S = SW_K * t * (1 / (3 t^2))^2 * (1 / w0)^3 * P(t^2),  SW_K = 9 (b + 1) / (3 sqrt(-3)) = 3 (b + 1) / sqrt(-3)
+_inv_s = pow(SQRT_M3, Q - 2, Q)
+SW_K = (3 * (B2[0] + 1) * _inv_s % Q, 3 * B2[1] * _inv_s % Q)
+
+
+def _check_sw_identity():
+    """numeric check of the identity on one value of t (plain ints, at import / build time)"""
+    t = (0x1234567, 0x89abcde)
+    tt = _f2i(t, t)
+    w0 = ((tt[0] + B2[0] + 1) % Q, (tt[1] + B2[1]) % Q)
+    inv = lambda a: _f2_inv_int(a)
+    w = _f2i(_f2i(t, (SQRT_M3, 0)), inv(w0))
+    x1 = _f2i(w, t)
+    x1 = ((SQRT_M3_M1_O2 - x1[0]) % Q, (-x1[1]) % Q)
+    x2 = ((-1 - x1[0]) % Q, (-x1[1]) % Q)
+    iw2 = inv(_f2i(w, w))
+    x3 = ((1 + iw2[0]) % Q, iw2[1])
+    g = lambda x: tuple((a + c) % Q for a, c in zip(_f2i(_f2i(x, x), x), B2))
+    prod = _f2i(_f2i(g(x1), g(x2)), g(x3))
+    i3t2 = inv(((3 * tt[0]) % Q, (3 * tt[1]) % Q))
+    iw0 = inv(w0)
+    S = _f2i(_f2i(_f2i(_f2i(SW_K, t), _f2i(i3t2, i3t2)), _f2i(_f2i(iw0, iw0), iw0)), _f2_poly_int(SW_P, tt))
+    assert _f2i(S, S) == prod, "Shallue-van de Woestijne product identity"
+
+
+_check_sw_identity()
 
 
 def sw_encode(prog, t, inv_w0, inv_3t2, w0):
@@ -105,14 +172,21 @@ def sw_encode(prog, t, inv_w0, inv_3t2, w0):
     x3 = prog.pack(x3.c0 + prog.const1(1), x3.c1)
     u1, n1, c1, ok1 = _candidate(prog, x1)
     u2, n2, c2, ok2 = _candidate(prog, x2)
-    u3, n3, c3, _ = _candidate(prog, x3)
+    u3 = x3.sqr() * x3 + prog.const2(B2)
+    # sqrt(norm(u3)) = N(S) c1 c2 whenever it is needed (neither u1 nor u2 a square), see above
+    tt = t.sqr()
+    pol = prog.const2(SW_P[0])
+    for coeff in SW_P[1:]:
+        pol = pol * tt + prog.const2(coeff)
+    iw0_3 = inv_w0.sqr() * inv_w0
+    big_s = ((t * prog.const2(SW_K)) * inv_3t2.sqr()) * (iw0_3 * pol)
+    alpha3 = (big_s.c0.sqr() + big_s.c1.sqr()) * (c1 * c2)
     use2 = ~ok1 & ok2
     use3 = ~ok1 & ~ok2
     x = prog.sel2(use3, x3, prog.sel2(use2, x2, x1))
     u = prog.sel2(use3, u3, prog.sel2(use2, u2, u1))
-    n = prog.sel1(use3, n3, prog.sel1(use2, n2, n1))
-    cc = prog.sel1(use3, c3, prog.sel1(use2, c2, c1))
-    y = _sqrt_selected(prog, u, n, cc)
+    alpha = prog.sel1(use3, alpha3, prog.sel1(use2, c2 * n2, c1 * n1))
+    y = _sqrt_selected(prog, u, alpha)
     flip = y.c1.gt_half() ^ parity
     y = prog.sel2(flip, -y, y)
     # w0 == 0 -> generator (no parity negation for Fq2, ec.py:466-470)
