@@ -110,21 +110,35 @@ def miller_loop_multi(prog, pairs):
 
     rs = [(xq, yq, one) for (_, _, xq, yq, _) in pairs]
     f = None
+
+    def absorb(f, lines):
+        """f times all the lines of one step; two lines at a time are multiplied with each other first"""
+        k = 0
+        if f is None:
+            l0, l1, l4 = lines[0]
+            f = F12(F6(l0, l1, zero), F6(zero, l4, zero))
+            k = 1
+        while k + 1 < len(lines):
+            f = f.mul_by_014_pair(lines[k], lines[k + 1])
+            k += 2
+        if k < len(lines):
+            f = f.mul_by_014(*lines[k])
+        return f
+
     for bit in X_BITS:
         if f is not None:
             f = f.sqr()
+        lines = []
         for k, (xp, yp, xq, yq, inf) in enumerate(pairs):
             rs[k], line = double_step(prog, rs[k], xp, yp)
-            l0, l1, l4 = guard(line, inf)
-            if f is None:
-                f = F12(F6(l0, l1, zero), F6(zero, l4, zero))
-            else:
-                f = f.mul_by_014(l0, l1, l4)
+            lines.append(guard(line, inf))
+        f = absorb(f, lines)
         if bit == "1":
+            lines = []
             for k, (xp, yp, xq, yq, inf) in enumerate(pairs):
                 rs[k], line = add_step(prog, rs[k], (xq, yq), xp, yp)
-                l0, l1, l4 = guard(line, inf)
-                f = f.mul_by_014(l0, l1, l4)
+                lines.append(guard(line, inf))
+            f = absorb(f, lines)
     return f
 
 

@@ -82,6 +82,15 @@ class F6:
         r2 = t1 + a2 * c0
         return F6(r0, r1, r2)
 
+    def mul_by_12(self, c1, c2):
+        """times (c1 v + c2 v^2): 5 Fq2 products"""
+        a0, a1, a2 = self.a0, self.a1, self.a2
+        t1, t2 = a1 * c1, a2 * c2
+        r0 = ((a1 + a2) * (c1 + c2) - t1 - t2).mul_xi()      # xi (a1 c2 + a2 c1)
+        r1 = a0 * c1 + t2.mul_xi()
+        r2 = a0 * c2 + t1
+        return F6(r0, r1, r2)
+
     def mul_by_1(self, c1):
         """times c1 v"""
         return F6((self.a2 * c1).mul_xi(), self.a0 * c1, self.a1 * c1)
@@ -175,6 +184,27 @@ class F12:
         t1 = self.c1.mul_by_1(l4)
         c1 = (self.c0 + self.c1).mul_by_01(l0, l1 + l4) - t0 - t1
         return F12(t0 + t1.mul_v(), c1)
+
+    def mul_by_014_pair(self, la, lb):
+        """times the product of TWO sparse line values (a0 + a1 v) + (a4 v) w and (b0 + b1 v) + (b4 v) w
+        (two Miller loops sharing their squarings): the lines are multiplied first, 6 Fq2 products,
+        using v^2 w^2 = v^3 = xi --
+            (a0 b0 + xi a4 b4) + (a0 b1 + a1 b0) v + a1 b1 v^2  +  ((a0 b4 + a4 b0) v + (a1 b4 + a4 b1) v^2) w
+        -- and the result, whose w-part has no constant term, costs 17 instead of 18 products against
+        self: 23 Fq2 products in all instead of 2 x 13."""
+        a0, a1, a4 = la
+        b0, b1, b4 = lb
+        p00, p11, p44 = a0 * b0, a1 * b1, a4 * b4
+        m01 = (a0 + a1) * (b0 + b1) - p00 - p11
+        m04 = (a0 + a4) * (b0 + b4) - p00 - p44
+        m14 = (a1 + a4) * (b1 + b4) - p11 - p44
+        c0 = F6(p00 + p44.mul_xi(), m01, p11)
+        d1, d2 = m04, m14                                   # c1 = d1 v + d2 v^2
+        t0 = self.c0 * c0
+        t1 = self.c1.mul_by_12(d1, d2)
+        s = self.c0 + self.c1
+        mid = s * F6(c0.a0, c0.a1 + d1, c0.a2 + d2) - t0 - t1
+        return F12(t0 + t1.mul_v(), mid)
 
     def inv(self, fp_inv):
         """(c0 - c1 w) / (c0^2 - v c1^2)  (bls_py/fields_t.py:328-337)"""
