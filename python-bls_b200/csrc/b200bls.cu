@@ -188,7 +188,7 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
 // Auto shape for an isolated batch of n items: more CTAs per SM raise throughput but also the
 // latency of one pass (measured pairing pass: 1 : 1.3 : 1.85 for 1 : 2 : 3 CTAs/SM), so the best
 // shape minimises passes x latency.  Pipelines that keep several batches in flight (bench.py)
-// select 3 explicitly.
+// select the wide shape (4) explicitly.
 int auto_ctas(size_t n) {
   static const double kLat[4] = {0, 1.0, 1.3, 1.85};
   int best = 1;
