@@ -217,8 +217,9 @@ def mul_by_x_abs(c, p):
     return acc
 
 
-def hash_to_g2(prog, buf):
-    """-> affine (x, y) of the hashed point (never infinity for honest inputs)"""
+def hash_to_g2(prog, buf, affine=True):
+    """-> affine (x, y) of the hashed point (never infinity for honest inputs); affine=False returns
+    the Jacobian point before the final inversion (callers that consume it inside the same program)"""
     c = Curve(prog, True)
     ts = []
     for j in range(2):
@@ -251,7 +252,7 @@ def hash_to_g2(prog, buf):
     t2 = c.add(c.add(t1, t0, complete=False), c.neg(p), complete=False)
     t3 = psi(prog, c.add(t0, p, complete=False))        # psi((a + 1) P)
     r = c.add(c.add(t2, c.neg(t3), complete=False), psi2(prog, c.double(p)), complete=False)
-    return c.to_affine(r)
+    return c.to_affine(r) if affine else r
 
 
 def build_hash_to_g2():

@@ -77,6 +77,30 @@ def add_step(prog, r, q, xp, yp):
     return (x3, y3, z3), (l0, l1, l4)
 
 
+def add_step_proj(prog, r, q, xp, yp):
+    """R <- R + Q with Q = (Xq, Yq, Zq) homogeneous projective: the affine-Q formulas applied to
+    (X Zq, Y Zq, Z Zq) and theta' = Y Zq - Yq Z, lam' = X Zq - Xq Z; the line is the affine one
+    times Zq^2, an Fq2 factor the final exponentiation removes."""
+    x, y, z = r
+    xq, yq, zq = q
+    xs, ys, zs = x * zq, y * zq, z * zq
+    theta = ys - yq * z
+    lam = xs - xq * z
+    l0 = theta * xq - lam * yq
+    l1 = -((theta * zq) * xp)
+    l4 = (lam * zq) * yp
+    c = theta.sqr()
+    d = lam.sqr()
+    e = lam * d
+    f = zs * c
+    g = xs * d
+    h = e + f - g.dbl()
+    x3 = lam * h
+    y3 = theta * (g - h) - e * ys
+    z3 = zs * e
+    return (x3, y3, z3), (l0, l1, l4)
+
+
 def miller_loop(prog, xp, yp, xq, yq):
     """f_{|x|,Q}(P) up to factors that the final exponentiation removes."""
     one = prog.const2((1, 0))
@@ -108,7 +132,11 @@ def miller_loop_multi(prog, pairs):
             return line
         return (prog.sel2(inf, one, line[0]), prog.sel2(inf, zero, line[1]), prog.sel2(inf, zero, line[2]))
 
-    rs = [(xq, yq, one) for (_, _, xq, yq, _) in pairs]
+    # a pair's Q is affine (xq, yq Fq2 values) or, when xq is a 3-tuple, homogeneous projective
+    def start(xq, yq):
+        return tuple(xq) if isinstance(xq, tuple) else (xq, yq, one)
+
+    rs = [start(xq, yq) for (_, _, xq, yq, _) in pairs]
     f = None
 
     def absorb(f, lines):
@@ -136,7 +164,10 @@ def miller_loop_multi(prog, pairs):
         if bit == "1":
             lines = []
             for k, (xp, yp, xq, yq, inf) in enumerate(pairs):
-                rs[k], line = add_step(prog, rs[k], (xq, yq), xp, yp)
+                if isinstance(xq, tuple):
+                    rs[k], line = add_step_proj(prog, rs[k], xq, xp, yp)
+                else:
+                    rs[k], line = add_step(prog, rs[k], (xq, yq), xp, yp)
                 lines.append(guard(line, inf))
             f = absorb(f, lines)
     return f
@@ -274,6 +305,28 @@ def build_verify_pair():
     ng = (prog.const1(NEG_G1[0]), prog.const1(NEG_G1[1]))
     f = miller_loop_multi(prog, [(ng[0], ng[1], xs, ys, inf_sig), (xk, yk, xh, yh, inf_pk)])
     e = final_exponentiation(prog, f, cubed=True)          # only compared with one
+    prog.store_flag(3, 0, f12_is_one(prog, e))
+    return prog
+
+
+def build_verify_full():
+    """hash-to-G2 and the verification core in ONE program: the hashed point goes into the Miller
+    loop as it leaves the cofactor clearing, projective, so its inversion (to_affine, ~490 M) is
+    never computed.  buffers: 0 = pk (G1 affine, 96 B), 1 = SHA stage output for the message hash
+    (256 B, csrc/sha256.cuh), 2 = sig (G2 affine, 192 B), 3 = result byte."""
+    from .hashg2 import hash_to_g2
+    prog = Program("verify_full")
+    prog.begin_body()
+    hx, hy, hz = hash_to_g2(prog, 1, affine=False)           # Jacobian: x = X / Z^2, y = Y / Z^3
+    hz2 = hz.sqr()
+    hq = (hx * hz, hy, hz2 * hz)                              # homogeneous: x = X' / Z', y = Y' / Z'
+    xk, yk = load_g1(prog, 0)
+    xs, ys = load_g2(prog, 2)
+    inf_pk = (xk.is_zero() & yk.is_zero()) | hq[2].is_zero()
+    inf_sig = xs.is_zero() & ys.is_zero()
+    ng = (prog.const1(NEG_G1[0]), prog.const1(NEG_G1[1]))
+    f = miller_loop_multi(prog, [(ng[0], ng[1], xs, ys, inf_sig), (xk, yk, hq, None, inf_pk)])
+    e = final_exponentiation(prog, f, cubed=True)
     prog.store_flag(3, 0, f12_is_one(prog, e))
     return prog
 

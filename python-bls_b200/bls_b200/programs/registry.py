@@ -26,6 +26,7 @@ PROGRAMS["pairing"] = pairing.build_pairing
 PROGRAMS["miller_loop"] = pairing.build_miller_only
 PROGRAMS["final_exp"] = pairing.build_final_exp
 PROGRAMS["verify_pair"] = pairing.build_verify_pair
+PROGRAMS["verify_full"] = pairing.build_verify_full
 PROGRAMS["miller_raw"] = pairing.build_miller_raw
 PROGRAMS["f12_prod1"] = pairing.build_f12_product_pass1
 PROGRAMS["f12_prod2"] = pairing.build_f12_product_pass2

@@ -543,12 +543,14 @@ int hash_to_g2_dev(const void* hashes, void* out, size_t n) {
 int verify_dev(const void* pk, const void* mh, const void* sig, void* ok, size_t n) {
   NEED_READY();
   if (n == 0) return 0;
-  int rc = ensure_scratch(4, (size_t)192 * n);
+  // SHA stage, then ONE program that hashes to G2 and verifies: the hashed point enters the Miller
+  // loop projective, its to_affine inversion is never computed
+  int rc = ensure_scratch(3, (size_t)256 * n);
   if (rc) return rc;
-  rc = hash_to_g2_dev(mh, cur().scratch[4].ptr, n);
+  rc = sha_stage_dev(mh, cur().scratch[3].ptr, n);
   if (rc) return rc;
-  VmBuf b[4] = {vb(pk, 96), vb(cur().scratch[4].ptr, 192), vb(sig, 192), vb(ok, 1)};
-  return launch_named("verify_pair", n, b, 4);
+  VmBuf b[4] = {vb(pk, 96), vb(cur().scratch[3].ptr, 256), vb(sig, 192), vb(ok, 1)};
+  return launch_named("verify_full", n, b, 4);
 }
 
 __global__ void and3_kernel(uint8_t* __restrict__ ok, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, long long n) {

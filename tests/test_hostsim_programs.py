@@ -100,6 +100,18 @@ def test_hash_and_verify_programs():
     asm = pairing.build_verify_pair().assemble(9, n_cold=4096, n_tmem=10)
     hostsim.run(asm, {0: pk, 1: Hm, 2: sig, 3: ok}, {0: 96, 1: 192, 2: 192, 3: 1}, len(tab), n_blocks=1, nt=4)
     assert [bool(x) for x in ok] == [t["ok"] for t in tab]
+    # the fused program (hash-to-G2 feeding the Miller loop as a projective point, no inversion)
+    tab = sg["verify_table"][:6]
+    pk = np.frombuffer(b"".join(ser1(O.g1_deserialize(bytes.fromhex(t["pk"]))) for t in tab), dtype=np.uint8).copy()
+    sig = np.frombuffer(b"".join(ser2(O.g2_deserialize(bytes.fromhex(t["sig"]))) for t in tab), dtype=np.uint8).copy()
+    hs = b"".join(bytes.fromhex(t["h"]) for t in tab)
+    sha = np.zeros(256 * len(tab), dtype=np.uint8)
+    lib.hs_sha_stage(hs, sha.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(len(tab)))
+    ok = np.full(len(tab), 9, dtype=np.uint8)
+    asm = pairing.build_verify_full().assemble(6, n_cold=4096, n_tmem=7)
+    hostsim.run(asm, {0: pk, 1: sha, 2: sig, 3: ok}, {0: 96, 1: 256, 2: 192, 3: 1}, len(tab), n_blocks=2, nt=3)
+    assert [bool(x) for x in ok] == [t["ok"] for t in tab]
+    assert any(t["ok"] for t in tab) and not all(t["ok"] for t in tab)
 
 
 @pytest.mark.parametrize("g2", [False, True])
