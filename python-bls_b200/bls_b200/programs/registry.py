@@ -28,6 +28,7 @@ PROGRAMS["final_exp"] = pairing.build_final_exp
 PROGRAMS["verify_pair"] = pairing.build_verify_pair
 PROGRAMS["verify_full"] = pairing.build_verify_full
 PROGRAMS["miller_raw"] = pairing.build_miller_raw
+PROGRAMS["miller_hash_raw"] = pairing.build_miller_hash_raw
 PROGRAMS["f12_prod1"] = pairing.build_f12_product_pass1
 PROGRAMS["f12_prod2"] = pairing.build_f12_product_pass2
 PROGRAMS["hash_to_g2"] = hashg2.build_hash_to_g2

@@ -487,6 +487,20 @@ int msm_dev(bool g2, const void* pts, const void* scalars, void* out, size_t n) 
 
 // ---- multi-pairing: Miller loops -> raw Fq12 per item -> product tree ------------------------
 // out576: big-endian product of the Miller values (not final-exponentiated)
+// product of the n raw Miller values in scratch[1] -> out576 (big-endian, not final-exponentiated)
+int raw_product_dev(void* out576, size_t n) {
+  const DevProgram* p1 = find_program("f12_prod1", n);
+  if (!p1) return B200BLS_E_PROGRAM;
+  int grid = grid_for(*p1, n);
+  int rc = ensure_scratch(2, (size_t)576 * grid);
+  if (rc) return rc;
+  VmBuf bb[2] = {vb(cur().scratch[1].ptr, (long long)n), vb(cur().scratch[2].ptr, grid)};
+  rc = launch_program(*p1, n, bb, 2, grid);
+  if (rc) return rc;
+  VmBuf bc[2] = {vb(cur().scratch[2].ptr, grid), vb(out576, 576)};
+  return launch_named("f12_prod2", (size_t)grid, bc, 2, 1);
+}
+
 int miller_product_dev(const void* P, const void* Q, void* out576, size_t n) {
   NEED_READY();
   if (n == 0) return fail(B200BLS_E_ARG, "pairing_multi needs at least one pair");
@@ -495,16 +509,26 @@ int miller_product_dev(const void* P, const void* Q, void* out576, size_t n) {
   VmBuf ba[3] = {vb(P, 96), vb(Q, 192), vb(cur().scratch[1].ptr, (long long)n)};
   rc = launch_named("miller_raw", n, ba, 3);
   if (rc) return rc;
-  const DevProgram* p1 = find_program("f12_prod1", n);
-  if (!p1) return B200BLS_E_PROGRAM;
-  int grid = grid_for(*p1, n);
-  rc = ensure_scratch(2, (size_t)576 * grid);
+  return raw_product_dev(out576, n);
+}
+
+int sha_stage_dev(const void* hashes, void* out256, size_t n);
+
+// Miller product of aggregate verification over m = n + 1 items in ONE launch: item 0 is the pair
+// (-G1, signature), given explicitly in Qgiven; items 1..n are (pk_i, H(mh_i)), hashed and paired
+// in the same program with H projective.  P: m x 96, mh: m x 32 (item 0 unused), Qgiven: m x 192
+// (zero where the hashed point is to be used).
+int aggregate_miller_dev(const void* P, const void* mh, const void* Qgiven, void* out576, size_t m) {
+  NEED_READY();
+  int rc = ensure_scratch(1, (size_t)576 * m);
+  if (!rc) rc = ensure_scratch(3, (size_t)256 * m);
   if (rc) return rc;
-  VmBuf bb[2] = {vb(cur().scratch[1].ptr, (long long)n), vb(cur().scratch[2].ptr, grid)};
-  rc = launch_program(*p1, n, bb, 2, grid);
+  rc = sha_stage_dev(mh, cur().scratch[3].ptr, m);
   if (rc) return rc;
-  VmBuf bc[2] = {vb(cur().scratch[2].ptr, grid), vb(out576, 576)};
-  return launch_named("f12_prod2", (size_t)grid, bc, 2, 1);
+  VmBuf bb[4] = {vb(P, 96), vb(cur().scratch[3].ptr, 256), vb(cur().scratch[1].ptr, (long long)m), vb(Qgiven, 192)};
+  rc = launch_named("miller_hash_raw", m, bb, 4);
+  if (rc) return rc;
+  return raw_product_dev(out576, m);
 }
 
 int sha_stage_dev(const void* hashes, void* out256, size_t n) {
@@ -1141,7 +1165,7 @@ int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8
       0x4e, 0x6f, 0x38, 0xba, 0x0e, 0xcb, 0x75, 0x1b, 0xad, 0x54, 0xdc, 0xd6, 0xb9, 0x39, 0xc2, 0xca};
   int rc;
   if ((rc = ensure_staging(0, 96 * (n + 1)))) return rc;
-  if ((rc = ensure_staging(1, 32 * n + 1))) return rc;
+  if ((rc = ensure_staging(1, 32 * (n + 1)))) return rc;
   if ((rc = ensure_staging(2, 192 * (n + 1)))) return rc;
   if ((rc = ensure_staging(3, 576 * 2))) return rc;
   uint8_t* dP = (uint8_t*)cur().staging[0].ptr;
@@ -1149,13 +1173,14 @@ int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8
   uint8_t* dQ = (uint8_t*)cur().staging[2].ptr;
   uint8_t* dF = (uint8_t*)cur().staging[3].ptr;
   CU(cudaMemcpyAsync(dP, kNegG1, 96, cudaMemcpyHostToDevice, STREAM));
+  CU(cudaMemsetAsync(dQ, 0, 192 * (n + 1), STREAM));
   CU(cudaMemcpyAsync(dQ, sig, 192, cudaMemcpyHostToDevice, STREAM));
+  CU(cudaMemsetAsync(dM, 0, 32, STREAM));
   if (n) {
     CU(cudaMemcpyAsync(dP + 96, pks, 96 * n, cudaMemcpyHostToDevice, STREAM));
-    CU(cudaMemcpyAsync(dM, mhs, 32 * n, cudaMemcpyHostToDevice, STREAM));
-    if ((rc = hash_to_g2_dev(dM, dQ + 192, n))) return rc;
+    CU(cudaMemcpyAsync(dM + 32, mhs, 32 * n, cudaMemcpyHostToDevice, STREAM));
   }
-  if ((rc = miller_product_dev(dP, dQ, dF, n + 1))) return rc;
+  if ((rc = aggregate_miller_dev(dP, dM, dQ, dF, n + 1))) return rc;
   VmBuf b[2] = {vb(dF, 576), vb(dF + 576, 576)};
   if ((rc = launch_named("final_exp", 1, b, 2))) return rc;
   uint8_t res[576];
