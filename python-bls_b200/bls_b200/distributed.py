@@ -55,6 +55,21 @@ def pairing_multi(P, Q, dist=None):
         lambda f: engine.final_exp_batch(f).tobytes())
 
 
+def aggregate_verify(sig, pks, hashes, rank=0, dist=None):
+    """aggregate verification with (pk_i, message hash_i) sharded across ranks: `pks`, `hashes` are
+    THIS rank's slice, `sig` the aggregate signature (used by rank 0 only).  Every rank hashes and
+    pairs its slice in one fused launch, the 576-byte Miller products are gathered, multiplied and
+    final-exponentiated once.  Returns the same bool on every rank."""
+    from . import engine
+    part = engine.aggregate_miller(sig if rank == 0 else None, pks, hashes).tobytes()
+    parts = gather_bytes(part, dist)
+    res = combine_miller_partials(
+        parts,
+        lambda a, b: engine.field_op(12, "mul", a, b).tobytes(),
+        lambda f: engine.final_exp_batch(f).tobytes())
+    return res == (1).to_bytes(48, "big") + bytes(528)
+
+
 def point_sum(points, g2, dist=None):
     """sum of points sharded across ranks (aggregate_sigs_simple / aggregate_pub_keys)"""
     from . import engine

@@ -184,6 +184,21 @@ def hash_to_g2(hashes):
     return out
 
 
+def aggregate_miller(sig, pks, hashes):
+    """[e(-G1, sig) *] prod_i miller(pk_i, H(hash_i)) as 576 bytes, not final-exponentiated: one
+    rank's partial of a sharded aggregate verification (sig = None: no signature pair)"""
+    _lib.init()
+    pks, hashes = as_u8(pks), as_u8(hashes)
+    n = hashes.size // 32
+    if pks.size != 96 * n or hashes.size != 32 * n:
+        raise ValueError("bad buffer sizes")
+    s = as_u8(sig, 192) if sig is not None else None
+    out = np.empty(576, dtype=np.uint8)
+    check(lib.b200bls_aggregate_miller(ptr(s) if s is not None else None, ptr(pks) if n else None,
+                                       ptr(hashes) if n else None, n, ptr(out)))
+    return out
+
+
 def verify_batch_wire(pks48, hashes, sigs96):
     """n x (serialised pk 48 B, message hash 32 B, serialised sig 96 B) -> n result bytes; inputs that
     do not decode are rejections"""

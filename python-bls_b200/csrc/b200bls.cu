@@ -1150,37 +1150,64 @@ int b200bls_verify_batch_wire_dev(const void* pk48, const void* mh, const void* 
   return verify_wire_dev(pk48, mh, sig96, ok, n);
 }
 
+namespace {
+const uint8_t kNegG1[96] = {
+    0x17, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f,
+    0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05, 0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58,
+    0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb,
+    0x11, 0x4d, 0x1d, 0x68, 0x55, 0xd5, 0x45, 0xa8, 0xaa, 0x7d, 0x76, 0xc8, 0xcf, 0x2e, 0x21, 0xf2,
+    0x67, 0x81, 0x6a, 0xef, 0x1d, 0xb5, 0x07, 0xc9, 0x66, 0x55, 0xb9, 0xd5, 0xca, 0xac, 0x42, 0x36,
+    0x4e, 0x6f, 0x38, 0xba, 0x0e, 0xcb, 0x75, 0x1b, 0xad, 0x54, 0xdc, 0xd6, 0xb9, 0x39, 0xc2, 0xca};
+
+// stages host inputs and leaves [e(-G1, sig) *] prod_i miller(pk_i, H(mh_i)) (big-endian, not
+// final-exponentiated) at staging[3]; sig may be null (a rank that does not own that pair)
+int aggregate_miller_host(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n) {
+  const size_t lead = sig ? 1 : 0, m = n + lead;
+  if (m == 0) return fail(B200BLS_E_ARG, "aggregate Miller product needs at least one pair");
+  int rc;
+  if ((rc = ensure_staging(0, 96 * m))) return rc;
+  if ((rc = ensure_staging(1, 32 * m))) return rc;
+  if ((rc = ensure_staging(2, 192 * m))) return rc;
+  if ((rc = ensure_staging(3, 576 * 2))) return rc;
+  uint8_t* dP = (uint8_t*)cur().staging[0].ptr;
+  uint8_t* dM = (uint8_t*)cur().staging[1].ptr;
+  uint8_t* dQ = (uint8_t*)cur().staging[2].ptr;
+  CU(cudaMemsetAsync(dQ, 0, 192 * m, STREAM));
+  if (sig) {
+    CU(cudaMemcpyAsync(dP, kNegG1, 96, cudaMemcpyHostToDevice, STREAM));
+    CU(cudaMemcpyAsync(dQ, sig, 192, cudaMemcpyHostToDevice, STREAM));
+    CU(cudaMemsetAsync(dM, 0, 32, STREAM));
+  }
+  if (n) {
+    CU(cudaMemcpyAsync(dP + 96 * lead, pks, 96 * n, cudaMemcpyHostToDevice, STREAM));
+    CU(cudaMemcpyAsync(dM + 32 * lead, mhs, 32 * n, cudaMemcpyHostToDevice, STREAM));
+  }
+  return aggregate_miller_dev(dP, dM, dQ, cur().staging[3].ptr, m);
+}
+}  // namespace
+
+// [e(-G1, sig) *] prod_i miller(pk_i, H(mh_i)), NOT final-exponentiated: one rank's partial of a
+// sharded aggregate verification (sig = NULL on the ranks that do not own the signature pair)
+int b200bls_aggregate_miller(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* out576) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_READY();
+  if (!out576 || (n && (!pks || !mhs))) return fail(B200BLS_E_ARG, "null buffer");
+  int rc = aggregate_miller_host(sig, pks, mhs, n);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out576, cur().staging[3].ptr, 576, cudaMemcpyDeviceToHost, STREAM));
+  CU(cudaStreamSynchronize(STREAM));
+  return 0;
+}
+
 // e(-G1, sig) * prod_i e(pk_i, H(mh_i)) == 1 for distinct message hashes and unit exponents:
 // the core of BLS.verify (bls_py/bls.py:194-201) after its host-side grouping
 int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok) {
   std::lock_guard<std::mutex> lk(g_mu);
   NEED_READY();
   if (!sig || !ok || (n && (!pks || !mhs))) return fail(B200BLS_E_ARG, "null buffer");
-  static const uint8_t kNegG1[96] = {
-      0x17, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f,
-      0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05, 0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58,
-      0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb,
-      0x11, 0x4d, 0x1d, 0x68, 0x55, 0xd5, 0x45, 0xa8, 0xaa, 0x7d, 0x76, 0xc8, 0xcf, 0x2e, 0x21, 0xf2,
-      0x67, 0x81, 0x6a, 0xef, 0x1d, 0xb5, 0x07, 0xc9, 0x66, 0x55, 0xb9, 0xd5, 0xca, 0xac, 0x42, 0x36,
-      0x4e, 0x6f, 0x38, 0xba, 0x0e, 0xcb, 0x75, 0x1b, 0xad, 0x54, 0xdc, 0xd6, 0xb9, 0x39, 0xc2, 0xca};
-  int rc;
-  if ((rc = ensure_staging(0, 96 * (n + 1)))) return rc;
-  if ((rc = ensure_staging(1, 32 * (n + 1)))) return rc;
-  if ((rc = ensure_staging(2, 192 * (n + 1)))) return rc;
-  if ((rc = ensure_staging(3, 576 * 2))) return rc;
-  uint8_t* dP = (uint8_t*)cur().staging[0].ptr;
-  uint8_t* dM = (uint8_t*)cur().staging[1].ptr;
-  uint8_t* dQ = (uint8_t*)cur().staging[2].ptr;
+  int rc = aggregate_miller_host(sig, pks, mhs, n);
+  if (rc) return rc;
   uint8_t* dF = (uint8_t*)cur().staging[3].ptr;
-  CU(cudaMemcpyAsync(dP, kNegG1, 96, cudaMemcpyHostToDevice, STREAM));
-  CU(cudaMemsetAsync(dQ, 0, 192 * (n + 1), STREAM));
-  CU(cudaMemcpyAsync(dQ, sig, 192, cudaMemcpyHostToDevice, STREAM));
-  CU(cudaMemsetAsync(dM, 0, 32, STREAM));
-  if (n) {
-    CU(cudaMemcpyAsync(dP + 96, pks, 96 * n, cudaMemcpyHostToDevice, STREAM));
-    CU(cudaMemcpyAsync(dM + 32, mhs, 32 * n, cudaMemcpyHostToDevice, STREAM));
-  }
-  if ((rc = aggregate_miller_dev(dP, dM, dQ, dF, n + 1))) return rc;
   VmBuf b[2] = {vb(dF, 576), vb(dF + 576, 576)};
   if ((rc = launch_named("final_exp", 1, b, 2))) return rc;
   uint8_t res[576];

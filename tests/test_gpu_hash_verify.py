@@ -176,3 +176,31 @@ def test_verify_from_wire_bytes():
     assert any(want) and not all(want)
     assert sum(1 for c in flips["cases"] if not c["decodes"]) > 0
     assert engine.verify_batch_wire(b"", b"", b"").size == 0
+
+
+def test_aggregate_miller_partials_combine_to_aggregate_verify():
+    """the sharded form: per-slice Miller partials (signature pair on the first slice only), their
+    Fq12 product and ONE final exponentiation give the same verdict as b200bls_aggregate_verify"""
+    from bls_b200 import engine, synth
+    from bls_b200.distributed import aggregate_verify as sharded
+    n = 37
+    sks = synth.scalars(71, n)
+    hs = synth.message_hashes(71, n)
+    g1 = np.frombuffer(ser1(O.G1), dtype=np.uint8)
+    sigs = engine.scalar_mul(engine.hash_to_g2(hs), sks, True)
+    agg = engine.point_sum(sigs, True)
+    pks = engine.scalar_mul(np.tile(g1, n), sks, False)
+    assert engine.aggregate_verify(agg, pks, hs)
+    cut = 15
+    parts = [engine.aggregate_miller(agg, pks[:96 * cut], hs[:cut]).tobytes(),
+             engine.aggregate_miller(None, pks[96 * cut:], hs[cut:]).tobytes()]
+    prod = engine.field_op(12, "mul", parts[0], parts[1])
+    one = (1).to_bytes(48, "big") + bytes(528)
+    assert engine.final_exp_batch(prod).tobytes() == one
+    assert sharded(agg, pks, hs) is True                      # world size 1
+    bad = hs.copy()
+    bad[3] = hs[4]
+    assert sharded(agg, pks, bad) is False
+    # only the signature pair: e(-G1, sig) alone is not one
+    lone = engine.aggregate_miller(agg, b"", b"")
+    assert engine.final_exp_batch(lone).tobytes() != one

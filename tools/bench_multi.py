@@ -106,12 +106,7 @@ one = O.f12_serialize(O.F12_ONE)
 
 
 def verify(grp):
-    Hl = engine.hash_to_g2(hs[lo:hi])
-    P, Q = pks, Hl
-    if rank == 0:                                               # the e(-G1, sigma) pair lives on rank 0
-        P = np.concatenate([np.frombuffer(neg_g1_b, dtype=np.uint8), pks])
-        Q = np.concatenate([np.frombuffer(agg, dtype=np.uint8), Hl])
-    return D.pairing_multi(P, Q, grp) == one
+    return D.aggregate_verify(agg, pks, hs[lo:hi], rank, grp)
 
 
 for name, grp in (("gloo", Group(gloo, "gloo")), ("nccl", Group(None, "nccl"))):
