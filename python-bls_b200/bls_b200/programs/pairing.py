@@ -423,6 +423,16 @@ def build_miller_only():
     return prog
 
 
+def build_final_exp_check():
+    """Fq12 (576 B) -> one byte: final_exponentiation(f) == 1, through the cheaper cube (see
+    final_exponentiation); the last step of aggregate verification"""
+    prog = Program("final_exp_check")
+    prog.begin_body()
+    f = F12.from_coeffs([prog.load2_be48(0, 96 * k) for k in range(6)])
+    prog.store_flag(1, 0, f12_is_one(prog, final_exponentiation(prog, f, cubed=True)))
+    return prog
+
+
 def build_final_exp():
     """Fq12 (576 B) -> Fq12 (576 B)"""
     prog = Program("final_exp")

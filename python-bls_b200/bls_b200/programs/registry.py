@@ -25,6 +25,7 @@ PROGRAMS["fq2_mul_chain"] = fieldops.build_fq2_mul_chain(512)
 PROGRAMS["pairing"] = pairing.build_pairing
 PROGRAMS["miller_loop"] = pairing.build_miller_only
 PROGRAMS["final_exp"] = pairing.build_final_exp
+PROGRAMS["final_exp_check"] = pairing.build_final_exp_check
 PROGRAMS["verify_pair"] = pairing.build_verify_pair
 PROGRAMS["verify_full"] = pairing.build_verify_full
 PROGRAMS["miller_raw"] = pairing.build_miller_raw

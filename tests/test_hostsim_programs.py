@@ -293,3 +293,29 @@ def test_instruction_fusion_patterns():
     assert all(o.d is not acc or not o.post for o in ops2)
     assert marks2["body"] is not None and marks2["epilogue"] is not None
     assert ops2[marks2["epilogue"]].name in ("DBL2", "STBE48")
+
+
+def test_final_exp_check_program():
+    """final_exp_check (the boolean, cubed final exponentiation of aggregate verification) on the host
+    build: miller(P, Q) * miller(-P, Q) exponentiates to one, miller(P, Q)^2 does not, and one does"""
+    g = load_golden("pairing_kat.json")
+    c = g["pairs"][1]
+    P, Q = _pq([c])
+    negP = P.copy()
+    y = (-int.from_bytes(bytes(P[48:96]), "big")) % O.Q
+    negP[48:96] = np.frombuffer(y.to_bytes(48, "big"), dtype=np.uint8)
+    ml = pairing.build_miller_only().assemble(18, n_cold=4096, n_tmem=21)
+    f = np.zeros(576 * 2, dtype=np.uint8)
+    hostsim.run(ml, {0: np.concatenate([P, negP]), 1: np.concatenate([Q, Q]), 2: f}, {0: 96, 1: 192, 2: 576}, 2,
+                n_blocks=1, nt=2)
+    mul = fieldops.build_field_op(12, "mul")().assemble(18, n_cold=4096, n_tmem=21)
+    a = np.concatenate([f[:576], f[:576]])
+    b = np.concatenate([f[576:], f[:576]])
+    prod = np.zeros(576 * 2, dtype=np.uint8)
+    hostsim.run(mul, {0: a, 1: b, 2: prod}, {0: 576, 1: 576, 2: 576}, 2, n_blocks=1, nt=2)
+    one = np.frombuffer((1).to_bytes(48, "big") + bytes(528), dtype=np.uint8)
+    chk = pairing.build_final_exp_check().assemble(6, n_cold=4096, n_tmem=7)
+    inp = np.concatenate([prod, one]).copy()
+    ok = np.full(3, 9, dtype=np.uint8)
+    hostsim.run(chk, {0: inp, 1: ok}, {0: 576, 1: 1}, 3, n_blocks=1, nt=3)
+    assert list(ok) == [1, 0, 1]
