@@ -199,6 +199,10 @@ int b200bls_verify_batch_wire_dev(const void* pk48, const void* mh, const void* 
  * *ok = (e(-G1, sig) * prod_i e(pk_i, H(mh_i)) == 1).  n + 1 Miller loops, one final
  * exponentiation.  pks are the per-message public-key sums the host-side grouping produced. */
 int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok);
+/* The same, enqueued on the selected library stream without waiting: several aggregate
+ * verifications overlap (b200bls_set_stream).  *ok is valid after b200bls_sync(); inputs must
+ * stay untouched until then. */
+int b200bls_aggregate_verify_async(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok);
 /* One rank's partial of a sharded aggregate verification: [e(-G1, sig) *] prod_i miller(pk_i,
  * H(mh_i)) as 576 bytes, NOT final-exponentiated (sig = NULL where the rank does not own the
  * signature pair).  Ranks exchange these, multiply them (b200bls_field_op_batch, level 12) and run

@@ -75,6 +75,7 @@ def _load():
         "b200bls_g2_msm": (i32, [vp, vp, vp, sz]),
         "b200bls_g2_msm_dev": (i32, [vp, vp, vp, sz]),
         "b200bls_aggregate_miller": (i32, [vp, vp, vp, sz, vp]),
+        "b200bls_aggregate_verify_async": (i32, [vp, vp, vp, sz, vp]),
         "b200bls_verify_batch_wire": (i32, [vp, vp, vp, vp, sz]),
         "b200bls_verify_batch_wire_dev": (i32, [vp, vp, vp, vp, sz]),
         "b200bls_hash_pks": (i32, [vp, ctypes.c_uint32, vp, sz]),

@@ -236,6 +236,51 @@ def aggregate_verify(sig, pks, hashes):
     return bool(ok[0])
 
 
+def aggregate_verify_many(jobs):
+    """several aggregate verifications in flight at once: jobs = [(sig 192 B, pks n x 96 B, hashes
+    n x 32 B), ...] are enqueued round-robin on the library's streams and waited for together ->
+    list of bool.  A 10,000-message job fills about a fifth of a B200, so sequential calls leave
+    most of it idle."""
+    _lib.init()
+    jobs = list(jobs)
+    if not jobs:
+        return []
+    n_streams = lib.b200bls_stream_count()
+    # result bytes in pinned memory: a device-to-host copy into pageable memory blocks the host
+    # until it has run, which would serialise the jobs
+    res_ptr = lib.b200bls_host_alloc(len(jobs))
+    if not res_ptr:
+        raise _lib.B200BlsError("pinned allocation failed")
+    res = np.ctypeslib.as_array(ctypes.cast(res_ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(len(jobs),))
+    res[:] = 0
+    keep = []
+    # throughput shape for jobs that share the GPU (the automatic choice is the lowest-latency shape,
+    # whose CTAs take a whole SM each and do not leave room for a second job)
+    prev_shape = lib.b200bls_get_ctas_per_sm()
+    if prev_shape == 0 and len(jobs) > 1:
+        check(lib.b200bls_set_ctas_per_sm(4))
+    try:
+        for k, (sig, pks, hashes) in enumerate(jobs):
+            sig, pks, hashes = as_u8(sig, 192), as_u8(pks), as_u8(hashes)
+            n = hashes.size // 32
+            if pks.size != 96 * n or hashes.size != 32 * n:
+                raise ValueError("bad buffer sizes")
+            if k >= n_streams and k % n_streams == 0:
+                check(lib.b200bls_sync())            # staging buffers are per stream: one job per stream in flight
+            keep.append((sig, pks, hashes))
+            check(lib.b200bls_set_stream(k % n_streams))
+            check(lib.b200bls_aggregate_verify_async(ptr(sig), ptr(pks) if n else None, ptr(hashes) if n else None,
+                                                     n, ctypes.c_void_p(res_ptr + k)))
+        check(lib.b200bls_sync())
+        out = [bool(v) for v in res]
+    finally:
+        check(lib.b200bls_set_stream(0))
+        lib.b200bls_sync()
+        lib.b200bls_set_ctas_per_sm(prev_shape)
+        lib.b200bls_host_free(ctypes.c_void_p(res_ptr))
+    return out
+
+
 class DeviceBuffer:
     """device memory owned by the library (for resident-data pipelines and benchmarks)"""
 

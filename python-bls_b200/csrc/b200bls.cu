@@ -66,7 +66,7 @@ struct Staging {
   size_t cap = 0;
 };
 
-constexpr int N_STREAMS = 4;
+constexpr int N_STREAMS = 8;
 
 // Everything a launch needs privately, so that launches on different streams can overlap:
 // the spill (cold) area, the item-block counter and the multi-stage scratch buffers.
@@ -1199,10 +1199,9 @@ int b200bls_aggregate_miller(const uint8_t* sig, const uint8_t* pks, const uint8
   return 0;
 }
 
-// e(-G1, sig) * prod_i e(pk_i, H(mh_i)) == 1 for distinct message hashes and unit exponents:
-// the core of BLS.verify (bls_py/bls.py:194-201) after its host-side grouping
-int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok) {
-  std::lock_guard<std::mutex> lk(g_mu);
+namespace {
+// enqueues the whole aggregate verification on the selected stream, result byte -> *ok (host)
+int aggregate_verify_enqueue(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok) {
   NEED_READY();
   if (!sig || !ok || (n && (!pks || !mhs))) return fail(B200BLS_E_ARG, "null buffer");
   int rc = aggregate_miller_host(sig, pks, mhs, n);
@@ -1210,11 +1209,28 @@ int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8
   uint8_t* dF = (uint8_t*)cur().staging[3].ptr;
   VmBuf b[2] = {vb(dF, 576), vb(dF + 576, 1)};
   if ((rc = launch_named("final_exp_check", 1, b, 2))) return rc;
-  uint8_t one = 0;
-  CU(cudaMemcpyAsync(&one, dF + 576, 1, cudaMemcpyDeviceToHost, STREAM));
-  CU(cudaStreamSynchronize(STREAM));
-  *ok = one ? 1 : 0;
+  CU(cudaMemcpyAsync(ok, dF + 576, 1, cudaMemcpyDeviceToHost, STREAM));
   return 0;
+}
+}  // namespace
+
+// e(-G1, sig) * prod_i e(pk_i, H(mh_i)) == 1 for distinct message hashes and unit exponents:
+// the core of BLS.verify (bls_py/bls.py:194-201) after its host-side grouping
+int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = aggregate_verify_enqueue(sig, pks, mhs, n, ok);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(STREAM));
+  return 0;
+}
+
+// the same without waiting: several aggregate verifications (on different library streams,
+// b200bls_set_stream) overlap -- a 10,000-message job fills a fifth of the GPU.  *ok is valid after
+// b200bls_sync(); the input buffers must stay untouched until then (pinned memory lets the copies
+// overlap other streams' kernels).
+int b200bls_aggregate_verify_async(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return aggregate_verify_enqueue(sig, pks, mhs, n, ok);
 }
 
 }  // extern "C"

@@ -204,3 +204,24 @@ def test_aggregate_miller_partials_combine_to_aggregate_verify():
     # only the signature pair: e(-G1, sig) alone is not one
     lone = engine.aggregate_miller(agg, b"", b"")
     assert engine.final_exp_batch(lone).tobytes() != one
+
+
+def test_aggregate_verify_many_overlapping_jobs():
+    """asynchronous aggregate verifications on all library streams: verdicts per job, good and bad"""
+    from bls_b200 import engine, synth
+    g1 = np.frombuffer(ser1(O.G1), dtype=np.uint8)
+    jobs, want = [], []
+    for j in range(7):
+        n = 20 + 13 * j
+        sks = synth.scalars(500 + j, n)
+        hs = synth.message_hashes(500 + j, n)
+        agg = engine.point_sum(engine.scalar_mul(engine.hash_to_g2(hs), sks, True), True)
+        pks = engine.scalar_mul(np.tile(g1, n), sks, False)
+        if j % 3 == 1:
+            hs = hs.copy()
+            hs[2] = hs[3]
+        jobs.append((agg, pks, hs))
+        want.append(j % 3 != 1)
+    assert engine.aggregate_verify_many(jobs) == want
+    assert [engine.aggregate_verify(*job) for job in jobs] == want
+    assert engine.aggregate_verify_many([]) == []

@@ -147,6 +147,22 @@ out["config4_aggregate_verify"] = {"n_messages": n4, "accepts": bool(ok), "rejec
                                    "first_call_seconds": wall}
 print(json.dumps(out["config4_aggregate_verify"]), flush=True)
 
+# ---- config 4, many jobs in flight: 16 aggregate verifications of n4 messages each on the library's streams
+# (the throughput shape: a 10,000-message job is then 27 wide CTAs, so four jobs share the GPU; the
+# default picks the lowest-latency shape, whose CTAs take a whole SM each)
+jobs = [(agg, pks, hs)] * 32
+out["config4_concurrent_jobs"] = {"jobs": len(jobs), "n_messages_each": n4}
+for shape in (0, 4):
+    check(lib.b200bls_set_ctas_per_sm(shape))
+    engine.aggregate_verify_many(jobs[:8])
+    t0 = time.perf_counter()
+    res = engine.aggregate_verify_many(jobs)
+    dt = time.perf_counter() - t0
+    out["config4_concurrent_jobs"]["shape_%d" % shape] = {"all_accept": all(res), "seconds": dt, "jobs_per_s": len(jobs) / dt,
+                                                          "miller_loops_per_s": len(jobs) * (n4 + 1) / dt}
+check(lib.b200bls_set_ctas_per_sm(0))
+print(json.dumps(out["config4_concurrent_jobs"]), flush=True)
+
 # ---- config 4 at a batch that fills the GPU (the 10,000-message case is latency bound: one
 # under-filled pass per stage plus ONE single-thread final exponentiation) -----------------------
 n4b = int(400_000 * scale)
