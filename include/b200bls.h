@@ -49,7 +49,7 @@ void b200bls_shutdown(void);
 const char* b200bls_last_error(void);
 int b200bls_sm_count(void);              /* SMs of the initialised device, 0 if none */
 int b200bls_sync(void);                  /* wait for the library stream */
-/* The library owns 4 CUDA streams.  *_dev and *_async entry points enqueue on the stream
+/* The library owns 8 CUDA streams.  *_dev and *_async entry points enqueue on the stream
  * selected here (default 0); launches on different streams overlap, which removes the tail-wave
  * loss between back-to-back batches.  b200bls_sync() waits for all of them; the timer brackets
  * all of them.  Synchronous host-buffer entry points run on the selected stream. */
