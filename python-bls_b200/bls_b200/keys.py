@@ -124,44 +124,58 @@ def _hd_halves(data, chain_code):
     return hmac256(data + bytes([0]), chain_code), hmac256(data + bytes([1]), chain_code)
 
 
-class ExtendedPrivateKey:
-    """BIP32-style hierarchical key (keys.py:167-253): child secret = parent secret + HMAC half"""
+HARDENED = 1 << 31                      # child numbers from here up commit to the secret key
+
+
+class _ExtendedKey:
+    """what the two halves of the BIP32-style hierarchy share (keys.py:167-316): a 45-byte header
+    -- version (4), depth (1), parent fingerprint (4), child number (4), chain code (32) -- in
+    front of the serialised key, and value semantics on the serialisation"""
+
+    def _set_header(self, version, depth, parent_fingerprint, child_number, chain_code):
+        self.version, self.depth = version, depth
+        self.parent_fingerprint, self.child_number = parent_fingerprint, child_number
+        self.chain_code = bytes(chain_code)
+
+    def _header(self):
+        return b"".join((self.version.to_bytes(4, "big"), bytes([self.depth]),
+                         self.parent_fingerprint.to_bytes(4, "big"), self.child_number.to_bytes(4, "big"),
+                         self.chain_code))
+
+    def _check_depth(self):
+        if self.depth >= 255:
+            raise Exception("Cannot go further than 255 levels")
+
+    def _child_header(self, i, tweak_data):
+        """-> (left HMAC half as an int mod n, header fields of child i)"""
+        left, right = _hd_halves(tweak_data + i.to_bytes(4, "big"), self.chain_code)
+        fields = (self.version, self.depth + 1, self.get_public_key().get_fingerprint(), i, right)
+        return int.from_bytes(left, "big") % GROUP_ORDER, fields
+
+    def size(self):
+        return len(self.serialize())
+
+    def __eq__(self, other):
+        return self.serialize() == other.serialize()
+
+    def __hash__(self):
+        return int.from_bytes(self.serialize(), "big")
+
+
+class ExtendedPrivateKey(_ExtendedKey):
+    """secret half: child secret = parent secret + left HMAC half (mod n)"""
     version = 1
     EXTENDED_PRIVATE_KEY_SIZE = 77
 
     def __init__(self, version, depth, parent_fingerprint, child_number, chain_code, private_key):
-        self.version = version
-        self.depth = depth
-        self.parent_fingerprint = parent_fingerprint
-        self.child_number = child_number
-        self.chain_code = chain_code
+        self._set_header(version, depth, parent_fingerprint, child_number, chain_code)
         self.private_key = private_key
 
     @staticmethod
     def from_seed(seed):
         left, right = _hd_halves(bytes(seed), b"BLS HD seed")
-        return ExtendedPrivateKey(ExtendedPrivateKey.version, 0, 0, 0, right,
-                                  PrivateKey(int.from_bytes(left, "big") % GROUP_ORDER))
-
-    def private_child(self, i):
-        if self.depth >= 255:
-            raise Exception("Cannot go further than 255 levels")
-        parent_pk = self.private_key.get_public_key()
-        # hardened children (i >= 2^31) commit to the secret key, the others to the public key
-        data = (self.private_key.serialize() if i >= 2 ** 31 else parent_pk.serialize()) + i.to_bytes(4, "big")
-        left, right = _hd_halves(data, self.chain_code)
-        sk = PrivateKey((int.from_bytes(left, "big") + self.private_key.value) % GROUP_ORDER)
-        return ExtendedPrivateKey(ExtendedPrivateKey.version, self.depth + 1, parent_pk.get_fingerprint(), i, right, sk)
-
-    def public_child(self, i):
-        return self.private_child(i).get_extended_public_key()
-
-    def _header(self):
-        return (self.version.to_bytes(4, "big") + bytes([self.depth]) + self.parent_fingerprint.to_bytes(4, "big") +
-                self.child_number.to_bytes(4, "big") + self.chain_code)
-
-    def get_extended_public_key(self):
-        return ExtendedPublicKey.from_bytes(self._header() + self.private_key.get_public_key().serialize())
+        root = PrivateKey(int.from_bytes(left, "big") % GROUP_ORDER)
+        return ExtendedPrivateKey(ExtendedPrivateKey.version, 0, 0, 0, right, root)
 
     def get_private_key(self):
         return self.private_key
@@ -169,61 +183,48 @@ class ExtendedPrivateKey:
     def get_public_key(self):
         return self.private_key.get_public_key()
 
-    def size(self):
-        return self.EXTENDED_PRIVATE_KEY_SIZE
+    def private_child(self, i):
+        self._check_depth()
+        committed = self.private_key.serialize() if i >= HARDENED else self.get_public_key().serialize()
+        tweak, fields = self._child_header(i, committed)
+        child = PrivateKey((tweak + self.private_key.value) % GROUP_ORDER)
+        return ExtendedPrivateKey(ExtendedPrivateKey.version, *fields[1:], child)
+
+    def public_child(self, i):
+        return self.private_child(i).get_extended_public_key()
+
+    def get_extended_public_key(self):
+        return ExtendedPublicKey.from_bytes(self._header() + self.get_public_key().serialize())
 
     def serialize(self):
         return self._header() + self.private_key.serialize()
 
-    def __eq__(self, other):
-        return self.serialize() == other.serialize()
 
-    def __hash__(self):
-        return int.from_bytes(self.serialize(), "big")
-
-
-class ExtendedPublicKey:
-    """public half of the hierarchy (keys.py:256-316): non-hardened children only,
-    child key = parent key + g1 * HMAC half (one scalar multiplication and one addition)"""
+class ExtendedPublicKey(_ExtendedKey):
+    """public half: non-hardened children only, child key = parent key + g1 * left HMAC half (one
+    scalar multiplication and one addition on the GPU)"""
     EXTENDED_PUBLIC_KEY_SIZE = 93
 
     def __init__(self, version, depth, parent_fingerprint, child_number, chain_code, public_key):
-        self.version = version
-        self.depth = depth
-        self.parent_fingerprint = parent_fingerprint
-        self.child_number = child_number
-        self.chain_code = chain_code
+        self._set_header(version, depth, parent_fingerprint, child_number, chain_code)
         self.public_key = public_key
 
     @staticmethod
     def from_bytes(serialized):
-        serialized = bytes(serialized)
-        return ExtendedPublicKey(int.from_bytes(serialized[:4], "big"), serialized[4],
-                                 int.from_bytes(serialized[5:9], "big"), int.from_bytes(serialized[9:13], "big"),
-                                 serialized[13:45], PublicKey.from_bytes(serialized[45:]))
-
-    def public_child(self, i):
-        if self.depth >= 255:
-            raise Exception("Cannot go further than 255 levels")
-        if i >= 2 ** 31:
-            raise Exception("Cannot derive hardened children from public key")
-        left, right = _hd_halves(self.public_key.serialize() + i.to_bytes(4, "big"), self.chain_code)
-        tweak = ec.generator_Fq() * (int.from_bytes(left, "big") % GROUP_ORDER)
-        return ExtendedPublicKey(self.version, self.depth + 1, self.public_key.get_fingerprint(), i, right,
-                                 PublicKey.from_g1(tweak + self.public_key.value))
+        raw = bytes(serialized)
+        words = [int.from_bytes(raw[a:b], "big") for a, b in ((0, 4), (4, 5), (5, 9), (9, 13))]
+        return ExtendedPublicKey(*words, raw[13:45], PublicKey.from_bytes(raw[45:]))
 
     def get_public_key(self):
         return self.public_key
 
-    def size(self):
-        return self.EXTENDED_PUBLIC_KEY_SIZE
+    def public_child(self, i):
+        self._check_depth()
+        if i >= HARDENED:
+            raise Exception("Cannot derive hardened children from public key")
+        tweak, fields = self._child_header(i, self.public_key.serialize())
+        child = PublicKey.from_g1(ec.generator_Fq() * tweak + self.public_key.value)
+        return ExtendedPublicKey(*fields, child)
 
     def serialize(self):
-        return (self.version.to_bytes(4, "big") + bytes([self.depth]) + self.parent_fingerprint.to_bytes(4, "big") +
-                self.child_number.to_bytes(4, "big") + self.chain_code + self.public_key.serialize())
-
-    def __eq__(self, other):
-        return self.serialize() == other.serialize()
-
-    def __hash__(self):
-        return int.from_bytes(self.serialize(), "big")
+        return self._header() + self.public_key.serialize()

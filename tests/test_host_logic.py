@@ -92,3 +92,21 @@ def test_lagrange_and_interpolation_match_reference():
         Threshold.lagrange_coeffs_at_zero([1, 1])
     with pytest.raises(AssertionError):
         Threshold.lagrange_coeffs_at_zero([0, 1])
+
+
+def test_extended_key_containers_without_gpu():
+    """header layout and value semantics of the HD-key containers (keys.py:167-316); derivation itself
+    needs the GPU and is covered by tests/test_gpu_ext.py"""
+    from bls_b200.keys import ExtendedPrivateKey, ExtendedPublicKey, PrivateKey, HARDENED
+    e = ExtendedPrivateKey(1, 3, 0xa4700b27, HARDENED + 77, bytes(range(32)), PrivateKey(0x1234))
+    raw = e.serialize()
+    assert len(raw) == e.size() == ExtendedPrivateKey.EXTENDED_PRIVATE_KEY_SIZE == 77
+    assert raw[:4] == (1).to_bytes(4, "big") and raw[4] == 3 and raw[5:9] == bytes.fromhex("a4700b27")
+    assert raw[9:13] == (HARDENED + 77).to_bytes(4, "big") and raw[13:45] == bytes(range(32))
+    assert raw[45:] == (0x1234).to_bytes(32, "big")
+    assert e == ExtendedPrivateKey(1, 3, 0xa4700b27, HARDENED + 77, bytes(range(32)), PrivateKey(0x1234))
+    assert hash(e) == int.from_bytes(raw, "big")
+    assert ExtendedPublicKey.EXTENDED_PUBLIC_KEY_SIZE == 93
+    deep = ExtendedPrivateKey(1, 255, 0, 0, bytes(32), PrivateKey(1))
+    with pytest.raises(Exception, match="255 levels"):
+        deep.private_child(0)
