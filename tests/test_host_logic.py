@@ -105,7 +105,7 @@ def test_extended_key_containers_without_gpu():
     assert raw[9:13] == (HARDENED + 77).to_bytes(4, "big") and raw[13:45] == bytes(range(32))
     assert raw[45:] == (0x1234).to_bytes(32, "big")
     assert e == ExtendedPrivateKey(1, 3, 0xa4700b27, HARDENED + 77, bytes(range(32)), PrivateKey(0x1234))
-    assert hash(e) == int.from_bytes(raw, "big")
+    assert hash(e) == hash(int.from_bytes(raw, "big"))
     assert ExtendedPublicKey.EXTENDED_PUBLIC_KEY_SIZE == 93
     deep = ExtendedPrivateKey(1, 255, 0, 0, bytes(32), PrivateKey(1))
     with pytest.raises(Exception, match="255 levels"):
