@@ -227,7 +227,7 @@ def run_gpu(args, rank, world, dist):
         aP[:] = hP
         aQ[:] = hQ
         host_sets.append((pP, pQ, pO, aO))
-    e2e_steps = max(2, min(args.steps, 6))
+    e2e_steps = max(2, min(args.steps, 24))
     for k in range(N_STREAMS):                                   # warm-up (staging allocation)
         check(lib.b200bls_set_stream(k))
         check(lib.b200bls_pairing_batch_async(host_sets[k][0], host_sets[k][1], host_sets[k][2], n))
@@ -356,7 +356,9 @@ def run_gpu(args, rank, world, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    # default 12: K batches of 65,536 are K x 170.7 item blocks on 148 SMs, and the timed region ends with
+    # a partly filled round (K = 5: 5.77 rounds -> 96 % of the steady-state rate, K = 12: 13.84 -> 98.9 %)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     args = ap.parse_args()
