@@ -348,7 +348,7 @@ def build_decompress(g2):
     (bls_py/keys.py:29-40): compressed x with the 'big y' flag in the top bit ->
     affine point.  buffers: 0 = compressed (96 / 48 B), 1 = out affine (192 / 96 B),
     2 = ok byte (0 where the reference raises 'No sqrt exists' / 'No y for point x')."""
-    from .hashg2 import _candidate, _sqrt_selected, ROOT_EXP
+    from .hashg2 import _candidate_with_root, _sqrt_selected, ROOT_EXP
     from .tower import fp_pow_chain
 
     def build():
@@ -357,7 +357,7 @@ def build_decompress(g2):
         big = prog.flag_bit(0, 255)                  # top bit of byte 0
         if g2:
             x = prog.load2_be48(0, 0, mask_top=True)
-            u, n, cc, ok = _candidate(prog, x)
+            u, n, cc, ok = _candidate_with_root(prog, x)
             y = _sqrt_selected(prog, u, cc * n)
             flip = y.c1.gt_half() ^ big              # want (y.c1 > q//2) == big
             y = prog.sel2(flip, -y, y)

@@ -65,8 +65,18 @@ def _root_pow(prog, n):
 
 
 def _candidate(prog, x):
-    """u = x^3 + b, and the data needed to decide / extract sqrt(u):
-    returns (u, c, ok) with c = norm(u)^((q-3)/4), ok = 'y_for_x(x) succeeds'"""
+    """u = x^3 + b, its norm n, and ok = 'y_for_x(x) succeeds' = u is a square in Fq2 = n is a
+    (nonzero) square in Fq -- decided by the Legendre-symbol instruction (integer pipe only),
+    not by an exponentiation"""
+    u = x.sqr() * x + prog.const2(B2)
+    n = u.c0.sqr() + u.c1.sqr()
+    ok = n.is_square() & ~u.c1.is_zero()
+    return u, n, ok
+
+
+def _candidate_with_root(prog, x):
+    """decompression: the candidate is always used, so ONE exponentiation c = n^((q-3)/4) gives the
+    character (c^2 n) and the root of the norm (c n) together: returns (u, n, c, ok)"""
     u = x.sqr() * x + prog.const2(B2)
     n = u.c0.sqr() + u.c1.sqr()
     c = _root_pow(prog, n)
@@ -90,73 +100,6 @@ def _sqrt_selected(prog, u, alpha):
     return prog.pack(y0, y1)
 
 
-# g(x1) g(x2) g(x3) = S^2 with S = (b + 1) P(t^2) / (3 sqrt(-3) t^3 w0^3), P of degree 6 (identity of the
-# Shallue-van de Woestijne map for y^2 = x^3 + b, checked symbolically and, below, numerically).
-# Hence norm(g(x3)) = (N(S) / sqrt(n1 n2))^2 and, when neither g(x1) nor g(x2) is a square,
-# 1 / sqrt(n1 n2) = c1 c2 for c_i = n_i^((q-3)/4): the third candidate needs no exponentiation.
-def _f2i(a, b2):
-    return ((a[0] * b2[0] - a[1] * b2[1]) % Q, (a[0] * b2[1] + a[1] * b2[0]) % Q)
-
-
-def _f2_poly_int(coeffs, x):
-    acc = (0, 0)
-    for c in coeffs:
-        acc = _f2i(acc, x)
-        acc = ((acc[0] + c[0]) % Q, (acc[1] + c[1]) % Q)
-    return acc
-
-
-def _sw_product_coeffs():
-    b = B2
-    pw = [(1, 0)]
-    for _ in range(6):
-        pw.append(_f2i(pw[-1], b))
-
-    def comb(*terms):                    # sum of k * b^e
-        r0 = r1 = 0
-        for k, e in terms:
-            r0 += k * pw[e][0]
-            r1 += k * pw[e][1]
-        return (r0 % Q, r1 % Q)
-
-    return [comb((1, 0)),
-            comb((6, 1), (-3, 0)),
-            comb((15, 2), (-6, 1), (6, 0)),
-            comb((20, 3), (6, 2), (-21, 1), (-7, 0)),
-            comb((15, 4), (24, 3), (9, 2), (6, 1), (6, 0)),
-            comb((6, 5), (21, 4), (24, 3), (6, 2), (-6, 1), (-3, 0)),
-            comb((1, 6), (6, 5), (15, 4), (20, 3), (15, 2), (6, 1), (1, 0))]
-
-
-SW_P = _sw_product_coeffs()              # P(T) = sum SW_P[k] T^(6-k), T = t^2
-# S = SW_K * t * (1 / (3 t^2))^2 * (1 / w0)^3 * P(t^2),  SW_K = 9 (b + 1) / (3 sqrt(-3)) = 3 (b + 1) / sqrt(-3)
-_inv_s = pow(SQRT_M3, Q - 2, Q)
-SW_K = (3 * (B2[0] + 1) * _inv_s % Q, 3 * B2[1] * _inv_s % Q)
-
-
-def _check_sw_identity():
-    """numeric check of the identity on one value of t (plain ints, at import / build time)"""
-    t = (0x1234567, 0x89abcde)
-    tt = _f2i(t, t)
-    w0 = ((tt[0] + B2[0] + 1) % Q, (tt[1] + B2[1]) % Q)
-    inv = lambda a: _f2_inv_int(a)
-    w = _f2i(_f2i(t, (SQRT_M3, 0)), inv(w0))
-    x1 = _f2i(w, t)
-    x1 = ((SQRT_M3_M1_O2 - x1[0]) % Q, (-x1[1]) % Q)
-    x2 = ((-1 - x1[0]) % Q, (-x1[1]) % Q)
-    iw2 = inv(_f2i(w, w))
-    x3 = ((1 + iw2[0]) % Q, iw2[1])
-    g = lambda x: tuple((a + c) % Q for a, c in zip(_f2i(_f2i(x, x), x), B2))
-    prod = _f2i(_f2i(g(x1), g(x2)), g(x3))
-    i3t2 = inv(((3 * tt[0]) % Q, (3 * tt[1]) % Q))
-    iw0 = inv(w0)
-    S = _f2i(_f2i(_f2i(_f2i(SW_K, t), _f2i(i3t2, i3t2)), _f2i(_f2i(iw0, iw0), iw0)), _f2_poly_int(SW_P, tt))
-    assert _f2i(S, S) == prod, "Shallue-van de Woestijne product identity"
-
-
-_check_sw_identity()
-
-
 def sw_encode(prog, t, inv_w0, inv_3t2, w0):
     """-> (x, y, is_infinity) on E'(Fq2); inv_w0 = 1/w0, inv_3t2 = 1/(3 t^2)"""
     c = Curve(prog, True)
@@ -170,22 +113,18 @@ def sw_encode(prog, t, inv_w0, inv_3t2, w0):
     x2 = prog.const2((Q - 1, 0)) - x1
     x3 = -(w0.sqr() * inv_3t2)                         # 1 / w^2 = - w0^2 / (3 t^2)
     x3 = prog.pack(x3.c0 + prog.const1(1), x3.c1)
-    u1, n1, c1, ok1 = _candidate(prog, x1)
-    u2, n2, c2, ok2 = _candidate(prog, x2)
+    u1, n1, ok1 = _candidate(prog, x1)
+    u2, n2, ok2 = _candidate(prog, x2)
+    # Shallue-van de Woestijne: g(x1) g(x2) g(x3) is a square, so the third candidate is one whenever
+    # the first two are not and needs no test (the reference reaches it through two exceptions)
     u3 = x3.sqr() * x3 + prog.const2(B2)
-    # sqrt(norm(u3)) = N(S) c1 c2 whenever it is needed (neither u1 nor u2 a square), see above
-    tt = t.sqr()
-    pol = prog.const2(SW_P[0])
-    for coeff in SW_P[1:]:
-        pol = pol * tt + prog.const2(coeff)
-    iw0_3 = inv_w0.sqr() * inv_w0
-    big_s = ((t * prog.const2(SW_K)) * inv_3t2.sqr()) * (iw0_3 * pol)
-    alpha3 = (big_s.c0.sqr() + big_s.c1.sqr()) * (c1 * c2)
+    n3 = u3.c0.sqr() + u3.c1.sqr()
     use2 = ~ok1 & ok2
     use3 = ~ok1 & ~ok2
     x = prog.sel2(use3, x3, prog.sel2(use2, x2, x1))
     u = prog.sel2(use3, u3, prog.sel2(use2, u2, u1))
-    alpha = prog.sel1(use3, alpha3, prog.sel1(use2, c2 * n2, c1 * n1))
+    n = prog.sel1(use3, n3, prog.sel1(use2, n2, n1))
+    alpha = _root_pow(prog, n) * n                     # sqrt(norm) of the SELECTED candidate only
     y = _sqrt_selected(prog, u, alpha)
     flip = y.c1.gt_half() ^ parity
     y = prog.sel2(flip, -y, y)

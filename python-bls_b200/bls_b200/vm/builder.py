@@ -72,6 +72,12 @@ class V1(Val):
         self.prog.emit("FGTHALF", f, self)
         return f
 
+    def is_square(self):
+        """nonzero quadratic residue: the Legendre symbol without an exponentiation"""
+        f = Flag(self.prog)
+        self.prog.emit("FSQR1", f, self)
+        return f
+
     def eq(self, o):
         f = Flag(self.prog)
         self.prog.emit("FEQ1", f, self, o)

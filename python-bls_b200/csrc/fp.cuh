@@ -276,6 +276,78 @@ FP_DEV bool fp_raw_gt(const fp& a, const fp& b) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Legendre symbol (x / q) == +1, i.e. x is a nonzero square, WITHOUT an exponentiation: the
+// binary Jacobi algorithm on 12-limb integers -- shifts, subtractions and selects only, so it
+// runs on the ALU pipe beside the other warps' multiplications (the Euler criterion costs
+// ~467 Montgomery products on the multiply pipe; this is ~550 rounds of ~75 ALU instructions).
+//   (2 / n) = -1  iff  n = 3, 5 (mod 8);   a, n odd, a < n: (a / n) = (n - a / a) * (-1 iff
+//   a = n = 3 (mod 4));   a >= n: (a / n) = (a - n / n).
+// The Montgomery form x R has the same character as x because R = 2^384 is a square.
+// Replaces the character tests inside the reference's Fq2.modsqrt when it is called on a
+// non-residue (bls_py/fields.py:463-482 via ec.py:255-269).
+// ---------------------------------------------------------------------------------------
+#ifdef B200BLS_HOSTSIM
+inline int fp_ctz(uint32_t x) { return __builtin_ctz(x); }
+inline uint32_t fp_funnel_r(uint32_t lo, uint32_t hi, int s) {
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31));
+}
+#else
+__device__ __forceinline__ int fp_ctz(uint32_t x) { return __ffs((int)x) - 1; }
+__device__ __forceinline__ uint32_t fp_funnel_r(uint32_t lo, uint32_t hi, int s) {
+  return __funnelshift_r(lo, hi, s);
+}
+#endif
+
+#ifdef B200BLS_HOSTSIM
+inline
+#else
+// out of line: a cold loop that must not perturb the interpreter's register allocation or sit
+// between its hot opcode bodies in the instruction cache
+__device__ __noinline__
+#endif
+bool fp_is_square(fp x) {
+  fp a, n;
+  fp_canonical(a, x);
+#pragma unroll
+  for (int i = 0; i < NL; i++) n.v[i] = QL(i);
+  uint32_t flip = 0;
+  for (;;) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < NL; i++) nz |= a.v[i];
+    if (nz == 0) break;
+    if (a.v[0] == 0) {  // 32 factors of two: an even number of sign changes
+#pragma unroll
+      for (int i = 0; i < NL - 1; i++) a.v[i] = a.v[i + 1];
+      a.v[NL - 1] = 0;
+      continue;
+    }
+    const int z = fp_ctz(a.v[0]);
+#pragma unroll
+    for (int i = 0; i < NL - 1; i++) a.v[i] = fp_funnel_r(a.v[i], a.v[i + 1], z);
+    a.v[NL - 1] >>= z;
+    flip ^= (uint32_t)z & ((n.v[0] >> 1) ^ (n.v[0] >> 2));  // bit 0: z odd and n = 3, 5 (mod 8)
+    // a is odd now
+    fp d;
+    d.v[0] = sub_cc(a.v[0], n.v[0]);
+#pragma unroll
+    for (int i = 1; i < NL; i++) d.v[i] = subc_cc(a.v[i], n.v[i]);
+    const uint32_t lt = subc(0, 0);  // all ones when a < n: swap (reciprocity), then n - a
+    flip ^= lt & ((a.v[0] & n.v[0]) >> 1);
+#pragma unroll
+    for (int i = 0; i < NL; i++) n.v[i] = lt ? a.v[i] : n.v[i];
+    a.v[0] = add_cc(d.v[0] ^ lt, lt & 1u);
+#pragma unroll
+    for (int i = 1; i < NL - 1; i++) a.v[i] = addc_cc(d.v[i] ^ lt, 0);
+    a.v[NL - 1] = addc(d.v[NL - 1] ^ lt, 0);
+  }
+  uint32_t rest = n.v[0] ^ 1u;  // gcd(x, q) = 1 always unless x = 0
+#pragma unroll
+  for (int i = 1; i < NL; i++) rest |= n.v[i];
+  return rest == 0 && (flip & 1u) == 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // Montgomery multiplication: r = a * b / R mod q, coarsely integrated operand scanning.
 //
 // State T = E + O * 2^32.  E = ev[0..11] holds 64-bit columns at even word positions,

@@ -319,3 +319,27 @@ def test_final_exp_check_program():
     ok = np.full(3, 9, dtype=np.uint8)
     hostsim.run(chk, {0: inp, 1: ok}, {0: 576, 1: 1}, 3, n_blocks=1, nt=3)
     assert list(ok) == [1, 0, 1]
+
+
+def test_legendre_symbol_instruction():
+    """FSQR1 (binary Jacobi algorithm on the limbs, csrc/fp.cuh fp_is_square) against Euler's
+    criterion: 0, 1, q - 1, small values, powers of two (whole-limb shifts), squares and their
+    non-residue multiples, inputs >= q on the wire (reduced on load)"""
+    import random
+    from bls_b200.vm.builder import Program
+    rnd = random.Random(11)
+    Q = O.Q
+    vals = [0, 1, 2, 3, 4, 5, Q - 1, Q - 2, Q, Q + 4, 1 << 32, 1 << 64, 1 << 352, 3 << 320, (1 << 383) - 1]
+    for _ in range(40):
+        r = rnd.randrange(1, Q)
+        vals += [r, r * r % Q, (Q - 1) * (r * r % Q) % Q, r >> rnd.randrange(380)]
+    prog = Program("fsqr1_test")
+    prog.begin_body()
+    prog.store_flag(1, 0, prog.load1_be48(0, 0).is_square())
+    asm = prog.assemble(6, n_cold=64, n_tmem=0)
+    a = np.frombuffer(b"".join(v.to_bytes(48, "big") for v in vals), dtype=np.uint8).copy()
+    out = np.full(len(vals), 9, dtype=np.uint8)
+    hostsim.run(asm, {0: a, 1: out}, {0: 48, 1: 1}, len(vals), n_blocks=1, nt=8)
+    want = [int(pow(v % Q, (Q - 1) // 2, Q) == 1) for v in vals]
+    assert list(out) == want
+    assert 0 < sum(want) < len(want)

@@ -101,6 +101,8 @@ def run(prog, bufs, n_items, n_threads=1, strides=None, out_bufs=None):
                     r = a[0] == 0 and a[1] == 0
                 elif nm == "FGTHALF":
                     r = a > HALF_Q
+                elif nm == "FSQR1":
+                    r = pow(a, (Q - 1) // 2, Q) == 1
                 elif nm == "FEQ1":
                     r = a == b
                 elif nm == "FEQ2":
