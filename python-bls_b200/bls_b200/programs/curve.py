@@ -12,7 +12,7 @@ canonical; Jacobian intermediates differ from the reference's whenever the order
 operations differs (tree reduction vs left fold).
 """
 from ..vm.builder import Program, Q
-from .tower import fp_inv_fermat, f2_inv
+from .tower import fp_inverter, f2_inv
 
 G1_GEN = (int("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac58"
               "6c55e83ff97a1aeffb3af00adb22c6bb", 16),
@@ -46,7 +46,7 @@ class Curve:
             self.prog.store1_be48(buf, off, v, block_only)
 
     def inv(self, a):
-        fp_inv = fp_inv_fermat(self.prog)
+        fp_inv = fp_inverter(self.prog)
         return f2_inv(a, fp_inv) if self.g2 else fp_inv(a)
 
     def mov(self, a):

@@ -4,7 +4,7 @@ Buffers: 0 = a, 1 = b (binary ops), 2 = out; elements are level * 48 bytes big-e
 reference's flat ZT order (bls_py/fields.py:273-278).
 """
 from ..vm.builder import Program
-from .tower import F6, F12, f2_inv, fp_inv_fermat
+from .tower import F6, F12, f2_inv, fp_inverter
 
 
 def _load(prog, buf, level):
@@ -42,7 +42,7 @@ def build_field_op(level, op):
         elif op == "neg":
             r = -a
         elif op == "inv":
-            fp_inv = fp_inv_fermat(prog)
+            fp_inv = fp_inverter(prog)
             r = fp_inv(a) if level == 1 else (f2_inv(a, fp_inv) if level == 2 else a.inv(fp_inv))
         else:
             raise ValueError(op)

@@ -20,7 +20,7 @@ program treats the candidate as "no y".
 """
 from ..vm.builder import Program, Q
 from .curve import Curve
-from .tower import f2_pow_int, fp_pow_chain, f2_inv, fp_inv_fermat
+from .tower import f2_pow_int, fp_pow_chain, f2_inv, fp_inverter
 
 X_ABS = 0xd201000000010000
 SQRT_M3 = 1586958781458431025242759403266842894121773480562120986020912974854563298150952611241517463240701
@@ -177,7 +177,7 @@ def hash_to_g2(prog, buf, affine=True):
     safe = [f[1] for f in facs]
     p01 = safe[0] * safe[1]
     p23 = safe[2] * safe[3]
-    inv_all = f2_inv(p01 * p23, fp_inv_fermat(prog))
+    inv_all = f2_inv(p01 * p23, fp_inverter(prog))
     i01 = inv_all * p23
     i23 = inv_all * p01
     invs = [i01 * safe[1], i01 * safe[0], i23 * safe[3], i23 * safe[2]]

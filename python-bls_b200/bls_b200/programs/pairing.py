@@ -14,7 +14,7 @@ is canonical, so this implementation is free to use
     i.e. five 64-bit exponentiations instead of one 1268-bit one.
 """
 from ..vm.builder import Program, Q
-from .tower import F6, F12, f12_one, fp_inv_fermat
+from .tower import F6, F12, f12_one, fp_inverter
 
 X_ABS = 0xd201000000010000
 X_BITS = bin(X_ABS)[3:]                     # below the leading one, MSB first
@@ -228,7 +228,7 @@ def final_exponentiation(prog, f, cyclotomic=True, cubed=False):
     the result has order dividing n and gcd(3, n) = 1, so r^3 == 1 iff r == 1.  With
     3 E = (a+1)^2 (q-a)(a^2+q^2-1) + 3 the first exponentiation is by a+1 (63 squarings) instead
     of by y = (a+1)/3 (96 squarings on its addition chain)."""
-    fp_inv = fp_inv_fermat(prog)
+    fp_inv = fp_inverter(prog)
     # easy part: f^((q^6 - 1)(q^2 + 1))
     t = f.conj() * f.inv(fp_inv)
     m = t.frob(prog, 2) * t

@@ -290,6 +290,8 @@ def fp_pow_chain(prog, a, e, window=4):
     return acc
 
 
-def fp_inv_fermat(prog):
-    """returns a function a -> a^(q-2) (0 -> 0, like bls_py/fields_t.py:47-55)"""
-    return lambda a: fp_pow_chain(prog, a, Q - 2)
+def fp_inverter(prog):
+    """returns a function a -> 1 / a in Fq (0 -> 0, like bls_py/fields_t.py:47-55): the INV1
+    instruction -- a binary almost-inverse (shifts and subtractions on the ALU pipe, beside the other
+    warps' multiplications) and two Montgomery products, instead of the 465 products of a^(q-2)"""
+    return lambda a: a.inv()

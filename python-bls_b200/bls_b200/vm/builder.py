@@ -62,6 +62,12 @@ class V1(Val):
         self.prog.emit("DBL1", r, self)
         return r
 
+    def inv(self):
+        """1 / self in Fq (0 -> 0)"""
+        r = V1(self.prog)
+        self.prog.emit("INV1", r, self)
+        return r
+
     def is_zero(self):
         f = Flag(self.prog)
         self.prog.emit("FZERO1", f, self)
@@ -105,6 +111,8 @@ class Half:
     is_zero = V1.is_zero
     gt_half = V1.gt_half
     eq = V1.eq
+    inv = V1.inv
+    is_square = V1.is_square
 
 
 class V2(Val):

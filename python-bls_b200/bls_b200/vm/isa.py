@@ -59,6 +59,7 @@ OPS = [
     ("XMOV2", "c2 c2 i", "d = cell a of thread (tid + b) mod block size"),
     ("SKIPZ", "f i -", "if no thread of the warp has flag[d]: skip the next a instructions"),
     ("FLDB", "f u i", "flag[d] = (byte b of the item's record in buffer a) != 0"),
+    ("INV1", "c1 c1 -", "d = 1 / a (0 -> 0): binary almost-inverse on the ALU pipe + two products"),
     ("FSQR1", "f c1 -", "flag[d] = a is a nonzero square mod q (Legendre symbol by the binary algorithm: ALU pipe only)"),
     # fused: one decode / load / store round instead of three
 ]

@@ -291,7 +291,13 @@ inline int fp_ctz(uint32_t x) { return __builtin_ctz(x); }
 inline uint32_t fp_funnel_r(uint32_t lo, uint32_t hi, int s) {
   return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31));
 }
+inline uint32_t fp_funnel_l(uint32_t lo, uint32_t hi, int s) {
+  return (uint32_t)(((((uint64_t)hi << 32) | lo) << (s & 31)) >> 32);
+}
 #else
+__device__ __forceinline__ uint32_t fp_funnel_l(uint32_t lo, uint32_t hi, int s) {
+  return __funnelshift_l(lo, hi, s);
+}
 __device__ __forceinline__ int fp_ctz(uint32_t x) { return __ffs((int)x) - 1; }
 __device__ __forceinline__ uint32_t fp_funnel_r(uint32_t lo, uint32_t hi, int s) {
   return __funnelshift_r(lo, hi, s);
@@ -469,6 +475,113 @@ __device__ __forceinline__ void fp_mul(fp& r, const fp& a, const fp& b) { r = fp
 #endif
 
 FP_DEV void fp_sqr(fp& r, const fp& a) { fp_mul(r, a, a); }
+
+// ---------------------------------------------------------------------------------------
+// Inversion: r = 1 / x in Fq, Montgomery form in and out, 0 -> 0  (reference: fq_invert,
+// bls_py/fields_t.py:47-55, extended Euclid on Python ints).
+//
+// Binary "almost inverse" (Kaliski) with the shifts batched by trailing-zero count.  State:
+// a, n (n odd) and cofactors ra, rn with
+//     n * ra + a * rn == q,     x * ra == sa * a * 2^k,     x * rn == -sa * n * 2^k   (mod q),
+// so every quantity stays in [0, q] and needs no modular reduction inside the loop: a round is
+// ~105 shift / subtract / select instructions on the ALU pipe, ~550 rounds per inversion, and
+// no multiplication at all -- the multiply pipe stays free for the other warps, where the
+// Fermat chain x^(q-2) occupied it for 465 Montgomery products.  At the end a = 0, n = 1 and
+// 1 / x == -sa * rn * 2^-k; the factor 2^-k and the Montgomery scaling are applied together by
+// two products: (r0 * 2^(768-k) / R) * (R^2 mod q) / R == r0 * 2^-k * R^2 (as integers mod q).
+// ---------------------------------------------------------------------------------------
+#ifdef B200BLS_HOSTSIM
+static const uint32_t kR2inv[NL] = B200BLS_R2_LIMBS;
+#define R2INVL(i) kR2inv[i]
+inline
+#else
+__device__ __forceinline__ constexpr uint32_t r2inv_limb(int i) {
+  constexpr uint32_t t[NL] = B200BLS_R2_LIMBS;
+  return t[i];
+}
+#define R2INVL(i) r2inv_limb(i)
+__device__ __noinline__
+#endif
+fp fp_inv(fp x) {
+  fp a, n, ra, rn;
+  fp_canonical(a, x);
+  fp_set_zero(ra);
+  fp_set_zero(rn);
+  ra.v[0] = 1;
+#pragma unroll
+  for (int i = 0; i < NL; i++) n.v[i] = QL(i);
+  uint32_t swaps = 0;
+  int k = 0;
+  for (;;) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < NL; i++) nz |= a.v[i];
+    if (nz == 0) break;
+    if (a.v[0] == 0) {  // a whole limb of zero bits
+#pragma unroll
+      for (int i = 0; i < NL - 1; i++) a.v[i] = a.v[i + 1];
+      a.v[NL - 1] = 0;
+#pragma unroll
+      for (int i = NL - 1; i > 0; i--) rn.v[i] = rn.v[i - 1];
+      rn.v[0] = 0;
+      k += 32;
+      continue;
+    }
+    const int z = fp_ctz(a.v[0]);
+#pragma unroll
+    for (int i = 0; i < NL - 1; i++) a.v[i] = fp_funnel_r(a.v[i], a.v[i + 1], z);
+    a.v[NL - 1] >>= z;
+#pragma unroll
+    for (int i = NL - 1; i > 0; i--) rn.v[i] = fp_funnel_l(rn.v[i - 1], rn.v[i], z);
+    rn.v[0] <<= z;
+    k += z;
+    // a, n odd: (a, n) <- (|a - n|, min(a, n)); the cofactor of the difference is ra + rn either way
+    fp d;
+    d.v[0] = sub_cc(a.v[0], n.v[0]);
+#pragma unroll
+    for (int i = 1; i < NL; i++) d.v[i] = subc_cc(a.v[i], n.v[i]);
+    const uint32_t lt = subc(0, 0);  // all ones when a < n
+    swaps ^= lt;
+    fp s;
+    fp_add_raw(s, ra, rn);
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      n.v[i] = lt ? a.v[i] : n.v[i];
+      rn.v[i] = lt ? ra.v[i] : rn.v[i];
+    }
+    ra = s;
+    a.v[0] = add_cc(d.v[0] ^ lt, lt & 1u);
+#pragma unroll
+    for (int i = 1; i < NL - 1; i++) a.v[i] = addc_cc(d.v[i] ^ lt, 0);
+    a.v[NL - 1] = addc(d.v[NL - 1] ^ lt, 0);
+  }
+  // 1 / x == sn * rn * 2^-k with sn = -1 initially and negated by every swap
+  fp r0;
+  if (swaps & 1u) {
+    r0 = rn;
+  } else {
+    r0.v[0] = sub_cc(QL(0), rn.v[0]);
+#pragma unroll
+    for (int i = 1; i < NL - 1; i++) r0.v[i] = subc_cc(QL(i), rn.v[i]);
+    r0.v[NL - 1] = subc(QL(NL - 1), rn.v[NL - 1]);
+  }
+  while (k < 385) {  // tiny inputs (x = 1: k = 381): bring 768 - k below 384
+    fp t;
+    fp_add_raw(t, r0, r0);
+    fp_canonical(r0, t);
+    k++;
+  }
+  const int e = 768 - k;  // 0 <= e <= 383 since k <= 2 * 381
+  fp w;
+#pragma unroll
+  for (int i = 0; i < NL; i++) w.v[i] = (i == (e >> 5)) ? (1u << (e & 31)) : 0u;
+  fp t, r2, r;
+  fp_mul(t, r0, w);
+#pragma unroll
+  for (int i = 0; i < NL; i++) r2.v[i] = R2INVL(i);
+  fp_mul(r, t, r2);
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------
 // Fq2 = Fq[u]/(u^2+1)  (reference: bls_py/fields.py:321-482, fields_t.py:75-161)

@@ -343,3 +343,31 @@ def test_legendre_symbol_instruction():
     want = [int(pow(v % Q, (Q - 1) // 2, Q) == 1) for v in vals]
     assert list(out) == want
     assert 0 < sum(want) < len(want)
+
+
+def test_inversion_instruction():
+    """INV1 (binary almost-inverse on the limbs + two Montgomery products, csrc/fp.cuh fp_inv) against
+    pow(x, q - 2, q): 0 -> 0, 1 (fewest shift rounds: the k < 385 fix-up), q - 1, powers of two
+    (whole-limb shifts), small and random values, inputs >= q on the wire"""
+    import random
+    from bls_b200.vm.builder import Program
+    rnd = random.Random(12)
+    Q = O.Q
+    vals = [0, 1, 2, 3, Q - 1, Q - 2, Q, Q + 1, 1 << 32, 1 << 64, 1 << 352, 3 << 320, (1 << 383) - 1, (Q + 1) // 2]
+    for _ in range(40):
+        r = rnd.randrange(1, Q)
+        vals += [r, r >> rnd.randrange(380), (r << 40) % Q]
+    prog = Program("inv1_test")
+    prog.begin_body()
+    x = prog.load1_be48(0, 0)
+    prog.store1_be48(1, 0, x.inv())
+    prog.store1_be48(1, 48, x.inv() * x)
+    asm = prog.assemble(6, n_cold=64, n_tmem=0)
+    a = np.frombuffer(b"".join(v.to_bytes(48, "big") for v in vals), dtype=np.uint8).copy()
+    out = np.zeros(96 * len(vals), dtype=np.uint8)
+    hostsim.run(asm, {0: a, 1: out}, {0: 48, 1: 96}, len(vals), n_blocks=1, nt=8)
+    raw = out.tobytes()
+    for i, v in enumerate(vals):
+        want = pow(v % Q, Q - 2, Q)
+        assert int.from_bytes(raw[96 * i:96 * i + 48], "big") == want, (i, hex(v))
+        assert int.from_bytes(raw[96 * i + 48:96 * i + 96], "big") == (0 if v % Q == 0 else 1), i

@@ -91,6 +91,8 @@ def run(prog, bufs, n_items, n_threads=1, strides=None, out_bufs=None):
                     r = 2 * a % Q
                 elif nm == "MOV1":
                     r = a
+                elif nm == "INV1":
+                    r = pow(a, Q - 2, Q)
                 elif nm == "LDC1":
                     r = prog.consts[op.a]
                 elif nm == "LDC2":
