@@ -64,3 +64,13 @@ def build_fq2_mul_chain(n_mul):
         prog.store2_be48(2, 0, a)
         return prog
     return build
+
+
+def build_is_square():
+    """buffers: 0 = Fq element (48 B), 1 = one byte: 1 iff the element is a nonzero square (the
+    Legendre-symbol instruction FSQR1 on its own; the product uses it inside hash-to-G2, where the
+    reference's y_for_x raises for a non-residue, bls_py/ec.py:255-269)"""
+    prog = Program("f1_is_square")
+    prog.begin_body()
+    prog.store_flag(1, 0, prog.load1_be48(0, 0).is_square())
+    return prog

@@ -21,6 +21,7 @@ PROGRAMS = {}
 for _level in (1, 2, 6, 12):
     for _op in ("add", "sub", "mul", "sqr", "neg", "inv"):
         PROGRAMS["f%d_%s" % (_level, _op)] = fieldops.build_field_op(_level, _op)
+PROGRAMS["f1_is_square"] = fieldops.build_is_square
 PROGRAMS["fq2_mul_chain"] = fieldops.build_fq2_mul_chain(512)
 PROGRAMS["pairing"] = pairing.build_pairing
 PROGRAMS["miller_loop"] = pairing.build_miller_only

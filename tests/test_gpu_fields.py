@@ -82,3 +82,34 @@ def test_inputs_are_reduced_mod_q():
 def test_empty_batch():
     from bls_b200 import engine
     assert engine.field_op(12, "mul", b"", b"").size == 0
+
+
+def test_inversion_edge_values():
+    """the binary almost-inverse behind every inversion (csrc/fp.cuh fp_inv): values with the fewest
+    and the most shift rounds, whole-limb shifts, lanes of one warp finishing at different rounds"""
+    from bls_b200 import engine
+    rnd = random.Random(77)
+    vals = [0, 1, 2, 3, Q - 1, Q - 2, (Q + 1) // 2, 1 << 32, 1 << 64, 1 << 352, 3 << 320, (1 << 380) + 1]
+    for _ in range(500):
+        r = rnd.randrange(1, Q)
+        vals += [r, r >> rnd.randrange(380)]
+    got = engine.field_op(1, "inv", b"".join(v.to_bytes(48, "big") for v in vals)).tobytes()
+    for i, v in enumerate(vals):
+        assert int.from_bytes(got[48 * i:48 * i + 48], "big") == pow(v, Q - 2, Q), (i, hex(v))
+
+
+def test_legendre_symbol_edge_values():
+    """FSQR1 (binary Jacobi algorithm, csrc/fp.cuh fp_is_square) vs Euler's criterion"""
+    from bls_b200 import engine
+    rnd = random.Random(78)
+    vals = [0, 1, 2, 3, 4, 5, Q - 1, Q - 2, Q, Q + 4, 1 << 32, 1 << 64, 1 << 352, 3 << 320, (1 << 383) - 1]
+    for _ in range(400):
+        r = rnd.randrange(1, Q)
+        vals += [r, r * r % Q, (Q - 1) * (r * r % Q) % Q, r >> rnd.randrange(380)]
+    n = len(vals)
+    a = engine.DeviceBuffer(48 * n).upload(np.frombuffer(b"".join(v.to_bytes(48, "big") for v in vals), dtype=np.uint8))
+    out = engine.DeviceBuffer(n)
+    engine.run_program_dev("f1_is_square", n, [a, out], [48, 1])
+    got = out.download()
+    want = [int(pow(v % Q, (Q - 1) // 2, Q) == 1) for v in vals]
+    assert list(got[:n]) == want
