@@ -14,7 +14,7 @@ is canonical, so this implementation is free to use
     i.e. five 64-bit exponentiations instead of one 1268-bit one.
 """
 from ..vm.builder import Program, Q
-from .tower import F6, F12, f12_one, fp_inverter
+from .tower import F6, F12, CompressedCyc, decompress_many, f12_one, fp_inverter
 
 X_ABS = 0xd201000000010000
 X_BITS = bin(X_ABS)[3:]                     # below the leading one, MSB first
@@ -183,6 +183,27 @@ def _pow_bits(f, e, sqr):
     return acc
 
 
+def _pow_x_compressed(prog, m, fp_inv):
+    """m^|x| for m in the cyclotomic subgroup: |x| = 2^63 + 2^62 + 2^60 + 2^57 + 2^48 + 2^16, so
+    m^|x| is the product of six members of ONE chain of 63 squarings of m.  The chain runs in
+    Karabina's compressed form (12 M per squaring instead of 18 M), the six snapshots are
+    decompressed together (one shared inversion = one INV1) and multiplied: about 1,030 M + 5
+    products instead of 1,134 M + 5 products for square-and-multiply on Granger-Scott squarings."""
+    bits = [i for i in range(64) if (X_ABS >> i) & 1]
+    assert bits[0] > 0
+    c = CompressedCyc.of(m)
+    snaps = []
+    for i in range(1, bits[-1] + 1):
+        c = c.sqr()
+        if i in bits:
+            snaps.append(c)
+    fs = decompress_many(prog, snaps, fp_inv)
+    acc = fs[0]
+    for f in fs[1:]:
+        acc = acc * f
+    return acc
+
+
 class _Pow:
     """a power m^e of a fixed base, carrying its exponent so that chains are self-checking"""
     __slots__ = ("v", "e", "sqr")
@@ -235,11 +256,12 @@ def final_exponentiation(prog, f, cyclotomic=True, cubed=False):
     # after the easy part m lies in the cyclotomic subgroup: cheap squarings, inverse = conj
     sqr = (lambda x: x.cyclotomic_sqr()) if cyclotomic else (lambda x: x.sqr())
     # hard part: m^(y (a+1) (q-a) (a^2+q^2-1)) * m
-    t1 = (_pow_bits(m, X_ABS, sqr) * m) if cubed else _pow_y(m, sqr)
-    t2 = _pow_bits(t1, X_ABS, sqr) * t1                    # ^(a+1)
-    t3 = t2.frob(prog, 1) * _pow_bits(t2, X_ABS, sqr).conj()      # ^(q-a)
-    t3a = _pow_bits(t3, X_ABS, sqr)
-    t4 = _pow_bits(t3a, X_ABS, sqr) * t3.frob(prog, 2) * t3.conj()   # ^(a^2+q^2-1)
+    pow_x = (lambda f: _pow_x_compressed(prog, f, fp_inv)) if cyclotomic else (lambda f: _pow_bits(f, X_ABS, sqr))
+    t1 = (pow_x(m) * m) if cubed else _pow_y(m, sqr)
+    t2 = pow_x(t1) * t1                                    # ^(a+1)
+    t3 = t2.frob(prog, 1) * pow_x(t2).conj()               # ^(q-a)
+    t3a = pow_x(t3)
+    t4 = pow_x(t3a) * t3.frob(prog, 2) * t3.conj()         # ^(a^2+q^2-1)
     if cubed:
         return t4 * (sqr(m) * m)
     return t4 * m

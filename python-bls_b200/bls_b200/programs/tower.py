@@ -229,6 +229,72 @@ class F12:
         return F12.from_coeffs(out)
 
 
+class CompressedCyc:
+    """Karabina's compressed form of an element of the cyclotomic subgroup: with Fq12 seen as
+    A + B w + C w^2 over Fq4 = Fq2[s], s = w^3 (A = z0 + z1 s, B = z2 + z3 s, C = z4 + z5 s, the
+    z_i of F12.cyclotomic_sqr), Granger-Scott squaring sends B -> 3 s C^2 + 2 conj(B) and
+    C -> 3 B^2 - 2 conj(C): B and C never look at A.  A run of squarings therefore needs 6 instead of
+    9 Fq2 squarings (12 M instead of 18 M) and four live values instead of six; A is recovered from
+    the subgroup relations when the run is over (decompress_many)."""
+    __slots__ = ("z2", "z3", "z4", "z5")
+
+    def __init__(self, z2, z3, z4, z5):
+        self.z2, self.z3, self.z4, self.z5 = z2, z3, z4, z5
+
+    @staticmethod
+    def of(f):
+        return CompressedCyc(f.c1.a0, f.c0.a2, f.c0.a1, f.c1.a2)
+
+    def sqr(self):
+        def fp4_sqr(a, b):
+            t0, t1 = a.sqr(), b.sqr()
+            return t1.mul_xi() + t0, (a + b).sqr() - t0 - t1
+
+        prog = self.z2.prog
+        t0, t1 = fp4_sqr(self.z2, self.z3)
+        t2, t3 = fp4_sqr(self.z4, self.z5)
+        return CompressedCyc(prog.tri2(t3.mul_xi(), self.z2, True), prog.tri2(t2, self.z3, False),
+                             prog.tri2(t0, self.z4, False), prog.tri2(t1, self.z5, True))
+
+
+def decompress_many(prog, items, fp_inv):
+    """[CompressedCyc] -> [F12] with ONE shared inversion.  From conj6(x) x = 1 and the
+    Granger-Scott identities (A B = s C^2 + conj(B), ...):
+        z1 = (3 z4^2 + xi z5^2 - 2 z3) / (4 z2)          (z2 != 0)
+        z1 = 2 z4 z5 / z3                                (z2 == 0)
+        z0 = xi (2 z1^2 + z2 z5 - 3 z3 z4) + 1
+    z2 = z3 = 0 only happens for x = 1 (no other element of the subgroup has B = 0), where the
+    numerator is 0 as well and the formulas give z1 = 0, z0 = 1 whatever stands in for 1 / 0;
+    zero denominators are replaced by 1 so that they cannot poison the shared inversion."""
+    one = prog.const2((1, 0))
+    nums, dens = [], []
+    for c in items:
+        s4, s5 = c.z4.sqr(), c.z5.sqr()
+        num_a = prog.tri2(s4, c.z3, False) + s5.mul_xi()
+        num_b = (c.z4 + c.z5).sqr() - s4 - s5
+        z2_zero = c.z2.is_zero()
+        nums.append(prog.sel2(z2_zero, num_b, num_a))
+        den = prog.sel2(z2_zero, c.z3, c.z2.dbl().dbl())
+        dens.append(prog.sel2(den.is_zero(), one, den))
+    prefix = [dens[0]]
+    for d in dens[1:]:
+        prefix.append(prefix[-1] * d)
+    inv = f2_inv(prefix[-1], fp_inv)
+    invs = [None] * len(dens)
+    for i in range(len(dens) - 1, 0, -1):
+        invs[i] = inv * prefix[i - 1]
+        inv = inv * dens[i]
+    invs[0] = inv
+    out = []
+    for c, num, di in zip(items, nums, invs):
+        z1 = num * di
+        u = c.z3 * c.z4
+        t = z1.sqr().dbl() + c.z2 * c.z5 - (u.dbl() + u)
+        z0 = t.mul_xi() + one
+        out.append(F12(F6(z0, c.z4, c.z3), F6(c.z2, z1, c.z5)))
+    return out
+
+
 def f12_one(prog):
     one = prog.const2((1, 0))
     zero = prog.const2((0, 0))

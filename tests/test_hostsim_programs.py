@@ -371,3 +371,48 @@ def test_inversion_instruction():
         want = pow(v % Q, Q - 2, Q)
         assert int.from_bytes(raw[96 * i:96 * i + 48], "big") == want, (i, hex(v))
         assert int.from_bytes(raw[96 * i + 48:96 * i + 96], "big") == (0 if v % Q == 0 else 1), i
+
+
+def test_compressed_decompression_branches():
+    """tower.decompress_many on the host simulation: the general branch, the z2 = 0 branch and the
+    all-zero case (x = 1), two items sharing one inversion, against the formulas evaluated with the
+    oracle's Fq2 arithmetic (inputs need not lie in the subgroup for this check)"""
+    import random
+    from bls_b200.vm.builder import Program
+    from bls_b200.programs.tower import CompressedCyc, decompress_many, fp_inverter
+    rnd = random.Random(21)
+    Q = O.Q
+    r2 = lambda: (rnd.randrange(Q), rnd.randrange(Q))
+    zero = (0, 0)
+    rows = [(r2(), r2(), r2(), r2(), r2(), r2(), r2(), r2()),           # both general
+            (zero, r2(), r2(), r2(), r2(), r2(), r2(), r2()),           # first item: z2 = 0
+            (r2(), r2(), r2(), r2(), zero, zero, zero, zero),           # second item: x = 1
+            (zero, zero, zero, zero, zero, r2(), r2(), r2())]
+    prog = Program("decompress_test")
+    prog.begin_body()
+    vals = [prog.load2_be48(0, 96 * k) for k in range(8)]
+    outs = decompress_many(prog, [CompressedCyc(*vals[:4]), CompressedCyc(*vals[4:])], fp_inverter(prog))
+    for j, f in enumerate(outs):
+        prog.store2_be48(1, 192 * j, f.c0.a0)
+        prog.store2_be48(1, 192 * j + 96, f.c1.a1)
+    asm = prog.assemble(6, n_cold=256, n_tmem=5)
+    ser = lambda a: a[0].to_bytes(48, "big") + a[1].to_bytes(48, "big")
+    inp = np.frombuffer(b"".join(ser(v) for row in rows for v in row), dtype=np.uint8).copy()
+    out = np.zeros(384 * len(rows), dtype=np.uint8)
+    hostsim.run(asm, {0: inp, 1: out}, {0: 768, 1: 384}, len(rows), n_blocks=1, nt=4)
+    raw = out.tobytes()
+    mul, add, sub, xi, k = O.f2_mul, O.f2_add, O.f2_sub, O.f2_mul_xi, O.f2_scale
+
+    def want(z2, z3, z4, z5):
+        if z2 != zero:
+            num, den = sub(add(k(mul(z4, z4), 3), xi(mul(z5, z5))), k(z3, 2)), k(z2, 4)
+        else:
+            num, den = k(mul(z4, z5), 2), z3
+        z1 = mul(num, O.f2_inv(den)) if den != zero else zero
+        z0 = add(xi(sub(add(k(mul(z1, z1), 2), mul(z2, z5)), k(mul(z3, z4), 3))), (1, 0))
+        return z0, z1
+    for i, row in enumerate(rows):
+        for j in range(2):
+            z0, z1 = want(*row[4 * j:4 * j + 4])
+            got = raw[384 * i + 192 * j:384 * i + 192 * j + 192]
+            assert got == ser(z0) + ser(z1), (i, j)

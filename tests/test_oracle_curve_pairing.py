@@ -138,3 +138,35 @@ def test_aggregation_sums():
         tot = sum(ks[:n]) % N
         assert O.g1_serialize(O.aff_mul(tot, O.G1)).hex() == s["g1_sum"]
         assert O.g2_serialize(O.aff_mul(tot, O.G2)).hex() == s["g2_sum"]
+
+
+def test_cyclotomic_subgroup_identities_behind_compressed_squaring():
+    """The relations bls_b200/programs/tower.py: decompress_many solves, checked with the ORACLE's
+    arithmetic on elements of the cyclotomic subgroup (f^((q^6-1)(q^2+1)) of random f).  With Fq12 =
+    A + B w + C w^2 over Fq2[s], s = w^3, z0..z5 as in F12.cyclotomic_sqr:
+        4 z2 z1 = 3 z4^2 + xi z5^2 - 2 z3        (general branch)
+        z0 z2 + xi z1 z3 = 2 xi z4 z5 + z2       (gives z1 = 2 z4 z5 / z3 on the z2 = 0 branch)
+        z0 = xi (2 z1^2 + z2 z5 - 3 z3 z4) + 1
+    and the compressed squaring itself (B, C of the square from B, C alone)."""
+    import random
+    rnd = random.Random(5)
+    Q = O.Q
+    for _ in range(3):
+        f = tuple(rnd.randrange(Q) for _ in range(12))
+        t = O.f12_mul(O.f12_frob(f, 6), O.f12_inv(f))
+        m = O.f12_mul(O.f12_frob(t, 2), t)
+        c = [(m[2 * k], m[2 * k + 1]) for k in range(6)]        # flat ZT order: c0.a0 c0.a1 c0.a2 c1.a0 c1.a1 c1.a2
+        z0, z4, z3, z2, z1, z5 = c
+        mul, add, sub, xi = O.f2_mul, O.f2_add, O.f2_sub, O.f2_mul_xi
+        k = lambda a, n: O.f2_scale(a, n)
+        assert k(mul(z2, z1), 4) == sub(add(k(mul(z4, z4), 3), xi(mul(z5, z5))), k(z3, 2))
+        assert add(mul(z0, z2), xi(mul(z1, z3))) == add(k(xi(mul(z4, z5)), 2), z2)
+        inner = sub(add(k(mul(z1, z1), 2), mul(z2, z5)), k(mul(z3, z4), 3))
+        assert z0 == add(xi(inner), (1, 0))
+        m2 = O.f12_mul(m, m)
+        d = [(m2[2 * j], m2[2 * j + 1]) for j in range(6)]
+        sq4 = lambda a, b: (add(mul(a, a), xi(mul(b, b))), k(mul(a, b), 2))
+        t0, t1 = sq4(z2, z3)
+        t2, t3 = sq4(z4, z5)
+        assert d[3] == add(k(xi(t3), 3), k(z2, 2)) and d[2] == sub(k(t2, 3), k(z3, 2))      # new z2, z3
+        assert d[1] == sub(k(t0, 3), k(z4, 2)) and d[5] == add(k(t1, 3), k(z5, 2))          # new z4, z5
