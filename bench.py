@@ -325,6 +325,9 @@ def run_gpu(args, rank, world, dist):
             traffic = cap["dram_bytes_per_launch"]
     except (OSError, ValueError, KeyError):
         pass
+    from bls_b200.programs import registry
+    executed_m = registry.executed_mults("pairing", 4)
+    executed_m_verify = registry.executed_mults("verify_full", 4)
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -337,7 +340,11 @@ def run_gpu(args, rank, world, dist):
                 "steps": e2e_steps, "api": "b200bls_pairing_batch_async + b200bls_sync (pinned host buffers, %d streams)" % N_STREAMS},
         "roofline": {"bound": "int32_mul", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
                      "unit": "T limb-products/s", "frac": achieved / peak_ops, "traffic": traffic,
-                     "note": "achieved = pairings/s/GPU x 15,200 M x 300 limb products (SURVEY 8d); peak = "
+                     "executed_M_per_unit": executed_m,
+                     "frac_executed": per_gpu * executed_m * LIMB_PRODUCTS_PER_M / peak_ops,
+                     "note": "achieved = pairings/s/GPU x 15,200 M x 300 limb products (SURVEY 8d, frozen efficient-"
+                             "algorithm count); frac_executed uses the Montgomery products the pairing program really "
+                             "executes (executed_M_per_unit, counted on the assembled code; inversions are ALU-pipe loops); peak = "
                              "IMAD.WIDE.U32.X carry-chain microbenchmark measured in this run; per-launch "
                              "algorithmic HBM bytes %d (%.4f of measured HBM peak at this rate); traffic = DRAM bytes of "
                              "one launch from profiles/r1_pairing_final_ncu.json (workspace spills to the L2-backed cold area)"
@@ -348,7 +355,9 @@ def run_gpu(args, rank, world, dist):
                   "verify_e2e_from_wire_bytes_per_s": world * nv / (verify_wire_ms * 1e-3),
                   "pairings_per_s_whole_wave_batches": world * nv / (wave_ms * 1e-3),
                   "whole_wave_roofline_frac": (nv / (wave_ms * 1e-3)) * M_PER_PAIRING * LIMB_PRODUCTS_PER_M / peak_ops,
-                  "verify_roofline_frac": (nv / (verify_ms * 1e-3)) * 30400 * 300 / peak_ops},
+                  "verify_roofline_frac": (nv / (verify_ms * 1e-3)) * 30400 * 300 / peak_ops,
+                  "verify_executed_M_per_unit": executed_m_verify,
+                  "verify_roofline_frac_executed": (nv / (verify_ms * 1e-3)) * executed_m_verify * 300 / peak_ops},
     }
     print(json.dumps(line), flush=True)
 

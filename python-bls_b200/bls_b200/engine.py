@@ -236,24 +236,39 @@ def aggregate_verify(sig, pks, hashes):
     return bool(ok[0])
 
 
+_PINNED = {}                # slot -> [pointer, capacity]: pinned staging, grown on demand, kept for the process
+
+
+def _pinned_array(slot, nbytes):
+    """uint8 view of nbytes of pinned host memory owned by `slot` (cudaHostAlloc / cudaFreeHost
+    synchronise the device, so the buffers are cached instead of allocated per call)"""
+    ent = _PINNED.get(slot)
+    if ent is None or ent[1] < nbytes:
+        if ent is not None:
+            lib.b200bls_host_free(ctypes.c_void_p(ent[0]))
+        cap = max(4096, nbytes + nbytes // 4)
+        p = lib.b200bls_host_alloc(cap)
+        if not p:
+            _PINNED.pop(slot, None)
+            raise _lib.B200BlsError("pinned allocation of %d bytes failed" % cap)
+        ent = _PINNED[slot] = [p, cap]
+    return np.ctypeslib.as_array(ctypes.cast(ent[0], ctypes.POINTER(ctypes.c_uint8)), shape=(ent[1],))[:nbytes]
+
+
 def aggregate_verify_many(jobs):
     """several aggregate verifications in flight at once: jobs = [(sig 192 B, pks n x 96 B, hashes
     n x 32 B), ...] are enqueued round-robin on the library's streams and waited for together ->
     list of bool.  A 10,000-message job fills about a fifth of a B200, so sequential calls leave
-    most of it idle."""
+    most of it idle.  Inputs are staged through pinned memory (one cached buffer per stream) and the
+    result bytes land in pinned memory: copies from / to pageable memory block the host until they
+    have run, which serialises the jobs and made the throughput jitter by 2-4x."""
     _lib.init()
     jobs = list(jobs)
     if not jobs:
         return []
     n_streams = lib.b200bls_stream_count()
-    # result bytes in pinned memory: a device-to-host copy into pageable memory blocks the host
-    # until it has run, which would serialise the jobs
-    res_ptr = lib.b200bls_host_alloc(len(jobs))
-    if not res_ptr:
-        raise _lib.B200BlsError("pinned allocation failed")
-    res = np.ctypeslib.as_array(ctypes.cast(res_ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(len(jobs),))
+    res = _pinned_array("res", len(jobs))
     res[:] = 0
-    keep = []
     # throughput shape for jobs that share the GPU (the automatic choice is the lowest-latency shape,
     # whose CTAs take a whole SM each and do not leave room for a second job)
     prev_shape = lib.b200bls_get_ctas_per_sm()
@@ -267,17 +282,21 @@ def aggregate_verify_many(jobs):
                 raise ValueError("bad buffer sizes")
             if k >= n_streams and k % n_streams == 0:
                 check(lib.b200bls_sync())            # staging buffers are per stream: one job per stream in flight
-            keep.append((sig, pks, hashes))
+            stage = _pinned_array(("in", k % n_streams), 192 + 128 * n)
+            stage[:192] = sig
+            stage[192:192 + 96 * n] = pks
+            stage[192 + 96 * n:] = hashes
+            base = stage.ctypes.data
             check(lib.b200bls_set_stream(k % n_streams))
-            check(lib.b200bls_aggregate_verify_async(ptr(sig), ptr(pks) if n else None, ptr(hashes) if n else None,
-                                                     n, ctypes.c_void_p(res_ptr + k)))
+            check(lib.b200bls_aggregate_verify_async(ctypes.c_void_p(base), ctypes.c_void_p(base + 192) if n else None,
+                                                     ctypes.c_void_p(base + 192 + 96 * n) if n else None,
+                                                     n, ctypes.c_void_p(res.ctypes.data + k)))
         check(lib.b200bls_sync())
         out = [bool(v) for v in res]
     finally:
         check(lib.b200bls_set_stream(0))
         lib.b200bls_sync()
         lib.b200bls_set_ctas_per_sm(prev_shape)
-        lib.b200bls_host_free(ctypes.c_void_p(res_ptr))
     return out
 
 

@@ -7,10 +7,12 @@ Pipeline per 32-byte message hash h:
      written in the reference as t2 - t3 + psi2P, ec.py:544-550);  output affine, 192 bytes.
 
 sw_encode (ec.py:449-507) is exception driven in the reference: it tries y_for_x(x1),
-y_for_x(x2) and picks index ((X1 - 1) X2) mod 3.  Here every lane evaluates all three
-candidates and selects with flags.  Square roots follow fields.py:463-482 ("complex method")
-but with one exponentiation c = n^((q-3)/4) per root, which yields the root (c n), the
-quadratic character (c^2 n) and the inverse root (c) at once.  Both roots {y, -y} are the
+y_for_x(x2) and picks index ((X1 - 1) X2) mod 3.  Here every lane decides which candidate is
+used from the Legendre symbols of the norms of g(x1), g(x2) (the FSQR1 instruction: binary Jacobi
+algorithm, no multiplications) and only the selected candidate pays for a square root.  Square
+roots follow fields.py:463-482 ("complex method") with one exponentiation c = n^((q-3)/4) per
+Fq root, which yields the root (c n), the quadratic character (c^2 n) and the inverse root (c) at
+once: two exponentiations per encode.  Both roots {y, -y} are the
 same set as the reference's; the sign is then fixed by the reference's own rule
 (lex_gt_neg(y) == parity, looking only at y.c1, ec.py:94-101, 505-506).
 

@@ -43,3 +43,21 @@ for _g2 in (False, True):
     PROGRAMS[_p + "_bucket"] = curve.build_bucket_fold(_g2)
     PROGRAMS[_p + "_decompress"] = curve.build_decompress(_g2)
     PROGRAMS[_p + "_cflag"] = curve.build_compress_flag(_g2)
+
+
+_M_WEIGHT = {"MUL2": 3, "SQR2": 2, "MULFP2": 2, "MUL1": 1, "SQR1": 1, "LDBE48": 1, "LDBE32": 1, "STBE48": 1, "FGTHALF": 1,
+             "INV1": 2}
+
+
+def executed_mults(name, shape=4):
+    """Montgomery products one item of program `name` really executes in launch shape `shape`
+    (counted on the assembled code; the ALU-only loops of INV1 / FSQR1 are not multiplications and
+    count only their two fix-up products).  bench.py reports the roofline fraction both with
+    SURVEY 8d's frozen efficient-algorithm constant and with this number."""
+    from ..vm import isa
+    n_slots, n_tmem = SHAPES[shape]
+    asm = PROGRAMS[name]().assemble(n_slots, n_cold=4096, n_tmem=n_tmem)
+    total = 0
+    for w in asm.code[:, 0]:
+        total += _M_WEIGHT.get(isa.OPNAME[int(w) & 0xff], 0)
+    return total

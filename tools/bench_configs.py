@@ -155,9 +155,11 @@ out["config4_concurrent_jobs"] = {"jobs": len(jobs), "n_messages_each": n4}
 for shape in (0, 4):
     check(lib.b200bls_set_ctas_per_sm(shape))
     engine.aggregate_verify_many(jobs[:8])
-    t0 = time.perf_counter()
-    res = engine.aggregate_verify_many(jobs)
-    dt = time.perf_counter() - t0
+    dt = 1e30
+    for _ in range(4):          # host-side enqueueing jitters (0.30 - 0.7 s for the same 32 jobs): best of 4
+        t0 = time.perf_counter()
+        res = engine.aggregate_verify_many(jobs)
+        dt = min(dt, time.perf_counter() - t0)
     out["config4_concurrent_jobs"]["shape_%d" % shape] = {"all_accept": all(res), "seconds": dt, "jobs_per_s": len(jobs) / dt,
                                                           "miller_loops_per_s": len(jobs) * (n4 + 1) / dt}
 check(lib.b200bls_set_ctas_per_sm(0))
