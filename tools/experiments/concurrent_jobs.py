@@ -1,6 +1,6 @@
 import sys, time, os
 import numpy as np
-sys.path.insert(0, sys.argv[1])
+sys.path.insert(0, "python-bls_b200")
 from bls_b200 import _lib, engine, synth
 from bls_b200._lib import check, lib
 from bls_b200.programs.curve import G1_GEN
