@@ -112,7 +112,7 @@ def miller_loop(prog, xp, yp, xq, yq):
             zero = prog.const2((0, 0))
             f = F12(F6(l0, l1, zero), F6(zero, l4, zero))
         else:
-            f = f.sqr().mul_by_014(l0, l1, l4)
+            f = f.sqr_x2().mul_by_014(l0, l1, l4)       # 2 f^2: the factor is an Fq constant
         if bit == "1":
             r, (l0, l1, l4) = add_step(prog, r, (xq, yq), xp, yp)
             f = f.mul_by_014(l0, l1, l4)
@@ -155,7 +155,7 @@ def miller_loop_multi(prog, pairs):
 
     for bit in X_BITS:
         if f is not None:
-            f = f.sqr()
+            f = f.sqr_x2()                              # 2 f^2: Fq factors die in the final exponentiation
         lines = []
         for k, (xp, yp, xq, yq, inf) in enumerate(pairs):
             rs[k], line = double_step(prog, rs[k], xp, yp)
