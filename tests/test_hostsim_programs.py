@@ -416,3 +416,36 @@ def test_compressed_decompression_branches():
             z0, z1 = want(*row[4 * j:4 * j + 4])
             got = raw[384 * i + 192 * j:384 * i + 192 * j + 192]
             assert got == ser(z0) + ser(z1), (i, j)
+
+
+def test_miller_squaring_and_compressed_power_against_oracle():
+    """F12.sqr_x2 (Chung-Hasan SQR3 over Fq4) == 2 f^2 on arbitrary f, and pairing._pow_x_compressed
+    (Karabina chain, shared decompression, top bits on Granger-Scott squarings) == m^|x| on elements
+    of the cyclotomic subgroup, both against the oracle's plain Fq12 arithmetic"""
+    import random
+    from bls_b200.vm.builder import Program
+    from bls_b200.programs.tower import F12, fp_inverter
+    rnd = random.Random(31)
+    Q = O.Q
+    fs = [tuple(rnd.randrange(Q) for _ in range(12)) for _ in range(3)]
+    ms = []
+    for f in fs:
+        t = O.f12_mul(O.f12_frob(f, 6), O.f12_inv(f))
+        ms.append(O.f12_mul(O.f12_frob(t, 2), t))
+    ser = lambda e: b"".join(int(c).to_bytes(48, "big") for c in e)
+    prog = Program("sqr_pow_test")
+    prog.begin_body()
+    f = F12.from_coeffs([prog.load2_be48(0, 96 * k) for k in range(6)])
+    m = F12.from_coeffs([prog.load2_be48(1, 96 * k) for k in range(6)])
+    pairing.store_f12(prog, 2, f.sqr_x2())
+    for k, c in enumerate(pairing._pow_x_compressed(prog, m, fp_inverter(prog)).coeffs()):
+        prog.store2_be48(3, 96 * k, c)
+    asm = prog.assemble(6, n_cold=4096, n_tmem=7)
+    a = np.frombuffer(b"".join(ser(x) for x in fs), dtype=np.uint8).copy()
+    b = np.frombuffer(b"".join(ser(x) for x in ms), dtype=np.uint8).copy()
+    o1 = np.zeros(576 * len(fs), dtype=np.uint8)
+    o2 = np.zeros(576 * len(fs), dtype=np.uint8)
+    hostsim.run(asm, {0: a, 1: b, 2: o1, 3: o2}, {0: 576, 1: 576, 2: 576, 3: 576}, len(fs), n_blocks=1, nt=4)
+    for i in range(len(fs)):
+        assert o1.tobytes()[576 * i:576 * (i + 1)] == ser(O.f12_scale(O.f12_mul(fs[i], fs[i]), 2)), i
+        assert o2.tobytes()[576 * i:576 * (i + 1)] == ser(O.f12_pow(ms[i], pairing.X_ABS)), i
