@@ -593,8 +593,10 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
     for i, op in enumerate(ops):
         cur_op[0] = i
         if i == section_marks["body"]:
+            emit("END")
             marks[0] = len(out)
         if i == section_marks["epilogue"]:
+            emit("END")
             marks[1] = len(out)
         if op.name == "XCHG":
             if skip_stack:
@@ -772,10 +774,14 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                         free_flags.append(flag_of.pop(r.id))
                 else:
                     release(r.id)
+    # every section ends with END: [prologue END | body END | epilogue END]
     if marks[0] is None:
-        marks[0] = 0
+        emit("END")
+        marks[0] = len(out)
     if marks[1] is None:
+        emit("END")
         marks[1] = len(out)
+    emit("END")
     code = np.array(out, dtype=np.uint16).reshape(-1, 4)
     stats["n_ins"] = len(out)
     return Assembled(prog.name, code, list(prog.consts), tuple(marks), n_slots, n_cold, stats)

@@ -61,7 +61,8 @@ OPS = [
     ("FLDB", "f u i", "flag[d] = (byte b of the item's record in buffer a) != 0"),
     ("INV1", "c1 c1 -", "d = 1 / a (0 -> 0): binary almost-inverse on the ALU pipe + two products"),
     ("FSQR1", "f c1 -", "flag[d] = a is a nonzero square mod q (Legendre symbol by the binary algorithm: ALU pipe only)"),
-    # fused: one decode / load / store round instead of three
+    ("END", "- - -", "end of a program section (prologue / body / epilogue): the paired kernel's interpreter loop "
+                     "stops here instead of comparing its program counter with a bound it would have to keep in a register"),
 ]
 
 OPCODE = {name: i for i, (name, _, _) in enumerate(OPS)}

@@ -19,6 +19,7 @@
 #include "../../include/b200bls.h"
 #include "sha256.cuh"
 #include "vm_kernel.cuh"
+#include "vm_kernel2.cuh"
 
 using namespace b200bls;
 
@@ -59,6 +60,10 @@ struct DevProgram {
   uint4* consts = nullptr;
   int n_ins = 0, body_start = 0, epi_start = 0, n_slots = 0, n_cold = 0, n_tmem = 0, ctas = 1;
   int threads = VM_NT;  // shape 4 ("wide"): one CTA of VM_NT_WIDE threads per SM
+  // paired kernel (vm_kernel2.cuh): two threads per item
+  int items = 128;            // items per CTA: 128 (256 threads, 1-3 CTAs per SM) or 192 (384 threads, 2 CTAs per SM)
+  int ctas2 = 1;              // CTAs per SM of the paired kernel
+  bool cross_thread = false;  // the program has block barriers / cross-thread reads: CTA-wide item blocks
 };
 
 struct Staging {
@@ -92,6 +97,7 @@ struct Context {
   std::map<std::string, DevProgram> programs;
   uint64_t launches = 0;
   int ctas_per_sm = 0;   // launch shape: CTAs of 128 threads per SM (programs/registry.py); 0 = auto
+  int kernel = 2;        // 2 = paired kernel (two threads per item, vm_kernel2.cuh); 1 = one thread per item
 };
 
 Context g_ctx;
@@ -122,9 +128,13 @@ struct SegArgs {
   const unsigned* idx;
 };
 
+int launch_program2(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int n_bufs, int grid_override,
+                    const SegArgs* seg);
+
 int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int n_bufs, int grid_override = 0,
                    const SegArgs* seg = nullptr) {
   Context& c = g_ctx;
+  if (c.kernel == 2) return launch_program2(pr, n_items, bufs, n_bufs, grid_override, seg);
   const int nt = pr.threads;
   if (seg) grid_override = (int)((n_items + nt - 1) / nt);  // one thread per segment, statically assigned
   long long blocks_needed = (long long)((n_items + nt - 1) / nt);
@@ -179,6 +189,95 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
       vm_kernel<true, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
     else
       vm_kernel<false, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
+  }
+  CU(cudaGetLastError());
+  c.launches++;
+  return 0;
+}
+
+// The paired kernel: two threads per item.  Per-item resources (slots, TMEM columns, cold slots) are
+// those the program was assembled for; a CTA holds pr.items items on 2 * pr.items threads.
+int launch_program2(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int n_bufs, int grid_override,
+                    const SegArgs* seg) {
+  Context& c = g_ctx;
+  const int items = pr.items, nt = 2 * items;
+  const long long cta_blocks = (long long)((n_items + items - 1) / items);
+  const long long max_grid = (long long)c.sm_count * pr.ctas2;
+  int grid = (int)(cta_blocks < max_grid ? cta_blocks : max_grid);
+  if (grid < 1) grid = 1;
+  if (seg) grid_override = (int)cta_blocks;  // one pair per segment, statically assigned
+  if (grid_override > 0) grid = grid_override;
+  const long long total = (long long)grid * nt;  // threads
+  StreamCtx& sc = cur();
+  const size_t cold_need = (size_t)pr.n_cold * 3 * sizeof(uint4) * total;
+  if (cold_need > sc.cold_bytes) {
+    CU(cudaStreamSynchronize(sc.stream));
+    if (sc.cold) cudaFree(sc.cold);
+    sc.cold = nullptr;
+    sc.cold_bytes = 0;
+    size_t want = (size_t)pr.n_cold * 3 * sizeof(uint4) * (size_t)max_grid * nt;
+    if (want < cold_need) want = cold_need;
+    cudaError_t e = cudaMalloc(&sc.cold, want);
+    if (e != cudaSuccess) return fail(B200BLS_E_NOMEM, "cold area cudaMalloc(%zu) failed", want);
+    sc.cold_bytes = want;
+  }
+  int* counter = sc.counters + (sc.counter_pos++ % N_COUNTERS);
+  CU(cudaMemsetAsync(counter, 0, sizeof(int), sc.stream));
+  VmParams p;
+  memset(&p, 0, sizeof(p));
+  p.code = pr.code;
+  p.body_start = pr.body_start;
+  p.epi_start = pr.epi_start;
+  p.n_ins = pr.n_ins;
+  p.consts = pr.consts;
+  p.cold = sc.cold;
+  p.n_items = (long long)n_items;
+  p.counter = counter;
+  if (seg) {
+    p.seg_start = seg->start;
+    p.seg_idx = seg->idx;
+  }
+  p.smem_cells = 2 * pr.n_slots;
+  const int warps = nt / 32;
+  if (!pr.cross_thread && !seg) {
+    // item blocks of 16 per warp.  An isolated batch (automatic shape) of w.f waves runs as ceil(w.f) EQUAL
+    // waves on fewer warps per CTA: each warp is faster at lower occupancy, the tail wave disappears.
+    p.warp_fetch = 1;
+    p.n_blocks = (long long)((n_items + VM2_ITEMS_PER_WARP - 1) / VM2_ITEMS_PER_WARP);
+    p.active_warps = warps;
+    if (c.ctas_per_sm == 0 && grid_override == 0) {
+      const long long cap = max_grid * warps;
+      const long long waves = (p.n_blocks + cap - 1) / cap;
+      long long act = (p.n_blocks + waves * grid - 1) / (waves * grid);
+      if (act < 1) act = 1;
+      if (act < warps) p.active_warps = (int)act;
+    }
+  } else {
+    p.n_blocks = cta_blocks;
+    p.active_warps = warps;
+  }
+  for (int i = 0; i < n_bufs && i < VM_MAX_BUFS; i++) p.bufs[i] = bufs[i];
+  const size_t smem = (size_t)pr.n_slots * 3 * sizeof(uint4) * nt;
+  const int groups = nt / 128;
+  p.tmem_group_cols = pr.n_tmem * 12;
+  const int cols = groups * p.tmem_group_cols;
+  p.tmem_cols = cols == 0 ? 0 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512));
+  if (cols > 512) return fail(B200BLS_E_PROGRAM, "%d TMEM slots do not fit 512 columns", pr.n_tmem);
+  if (nt == VM2_NT_WIDE) {
+    if (seg)
+      vm2_kernel<true, VM2_NT_WIDE, 2, true><<<grid, nt, smem, sc.stream>>>(p);
+    else
+      vm2_kernel<true, VM2_NT_WIDE, 2><<<grid, nt, smem, sc.stream>>>(p);
+  } else if (p.tmem_cols) {
+    if (seg)
+      vm2_kernel<true, VM2_NT, 3, true><<<grid, nt, smem, sc.stream>>>(p);
+    else
+      vm2_kernel<true, VM2_NT, 3><<<grid, nt, smem, sc.stream>>>(p);
+  } else {
+    if (seg)
+      vm2_kernel<false, VM2_NT, 3, true><<<grid, nt, smem, sc.stream>>>(p);
+    else
+      vm2_kernel<false, VM2_NT, 3><<<grid, nt, smem, sc.stream>>>(p);
   }
   CU(cudaGetLastError());
   c.launches++;
@@ -275,8 +374,9 @@ int run_dev(const char* name, size_t n, const DevBuf* db, int n_bufs) {
 
 
 int grid_for(const DevProgram& pr, size_t n_items) {
-  long long blocks_needed = (long long)((n_items + pr.threads - 1) / pr.threads);
-  long long max_grid = (long long)g_ctx.sm_count * pr.ctas;
+  const int per_cta = g_ctx.kernel == 2 ? pr.items : pr.threads;
+  long long blocks_needed = (long long)((n_items + per_cta - 1) / per_cta);
+  long long max_grid = (long long)g_ctx.sm_count * (g_ctx.kernel == 2 ? pr.ctas2 : pr.ctas);
   long long g = blocks_needed < max_grid ? blocks_needed : max_grid;
   return g < 1 ? 1 : (int)g;
 }
@@ -708,6 +808,12 @@ int b200bls_init(int device) {
   CU(cudaFuncSetAttribute(vm_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   CU(cudaFuncSetAttribute(vm_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   CU(cudaFuncSetAttribute(vm_kernel<true, 1, VM_NT_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  CU(cudaFuncSetAttribute(vm2_kernel<false, VM2_NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  CU(cudaFuncSetAttribute(vm2_kernel<true, VM2_NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  CU(cudaFuncSetAttribute(vm2_kernel<true, VM2_NT_WIDE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+  CU(cudaFuncSetAttribute(vm2_kernel<false, VM2_NT, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  CU(cudaFuncSetAttribute(vm2_kernel<true, VM2_NT, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  CU(cudaFuncSetAttribute(vm2_kernel<true, VM2_NT_WIDE, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
   // parse the embedded program blob
   const unsigned char* blob = _binary_programs_bin_start;
   size_t blob_len = (size_t)(_binary_programs_bin_end - _binary_programs_bin_start);
@@ -728,9 +834,19 @@ int b200bls_init(int device) {
     dp.n_cold = (int)en.n_cold;
     dp.n_tmem = (int)en.n_tmem;
     dp.ctas = (int)en.ctas;
-    if (dp.ctas == 4) {  // shape id 4 = the wide shape: one CTA of 384 threads per SM
+    dp.ctas2 = dp.ctas;
+    if (dp.ctas == 4) {  // shape id 4 = the wide shape: 384 items per SM (one CTA of 384 threads, or two CTAs of 192 pairs)
       dp.ctas = 1;
       dp.threads = VM_NT_WIDE;
+      dp.ctas2 = 2;
+      dp.items = VM2_NT_WIDE / 2;
+    }
+    {
+      const unsigned char* code = blob + en.code_off;
+      for (uint32_t k = 0; k < en.n_ins; k++) {
+        const int op = code[8 * k];
+        if (op == OP_SYNC || op == OP_XMOV2 || op == OP_STRAWB2) dp.cross_thread = true;
+      }
     }
     size_t code_bytes = (size_t)(en.n_ins + 1) * sizeof(uint2);
     size_t const_bytes = (size_t)en.n_consts * 3 * sizeof(uint4);
@@ -745,6 +861,8 @@ int b200bls_init(int device) {
     nm[32] = 0;
     c.programs[nm] = dp;
   }
+  const char* kenv = getenv("B200BLS_KERNEL");
+  if (kenv && (kenv[0] == '1' || kenv[0] == '2')) c.kernel = kenv[0] - '0';
   const char* env = getenv("B200BLS_CTAS_PER_SM");
   if (env && env[0] >= '0' && env[0] <= '4') c.ctas_per_sm = env[0] - '0';
   c.device = device;

@@ -333,19 +333,22 @@ bool fp_is_square(fp x) {
     for (int i = 0; i < NL - 1; i++) a.v[i] = fp_funnel_r(a.v[i], a.v[i + 1], z);
     a.v[NL - 1] >>= z;
     flip ^= (uint32_t)z & ((n.v[0] >> 1) ^ (n.v[0] >> 2));  // bit 0: z odd and n = 3, 5 (mod 8)
-    // a is odd now
-    fp d;
-    d.v[0] = sub_cc(a.v[0], n.v[0]);
+    // a is odd now: (a, n) <- (|a - n|, min(a, n)), in place (the state is two values, not three: this
+    // function has to fit the paired kernel's 80-register budget next to its caller's live state)
+    const uint32_t a0 = a.v[0];
+    a.v[0] = sub_cc(a.v[0], n.v[0]);
 #pragma unroll
-    for (int i = 1; i < NL; i++) d.v[i] = subc_cc(a.v[i], n.v[i]);
+    for (int i = 1; i < NL; i++) a.v[i] = subc_cc(a.v[i], n.v[i]);
     const uint32_t lt = subc(0, 0);  // all ones when a < n: swap (reciprocity), then n - a
-    flip ^= lt & ((a.v[0] & n.v[0]) >> 1);
+    flip ^= lt & ((a0 & n.v[0]) >> 1);
+    n.v[0] = add_cc(n.v[0], a.v[0] & lt);  // n + (a - n) = the old a
 #pragma unroll
-    for (int i = 0; i < NL; i++) n.v[i] = lt ? a.v[i] : n.v[i];
-    a.v[0] = add_cc(d.v[0] ^ lt, lt & 1u);
+    for (int i = 1; i < NL - 1; i++) n.v[i] = addc_cc(n.v[i], a.v[i] & lt);
+    n.v[NL - 1] = addc(n.v[NL - 1], a.v[NL - 1] & lt);
+    a.v[0] = add_cc(a.v[0] ^ lt, lt & 1u);
 #pragma unroll
-    for (int i = 1; i < NL - 1; i++) a.v[i] = addc_cc(d.v[i] ^ lt, 0);
-    a.v[NL - 1] = addc(d.v[NL - 1] ^ lt, 0);
+    for (int i = 1; i < NL - 1; i++) a.v[i] = addc_cc(a.v[i] ^ lt, 0);
+    a.v[NL - 1] = addc(a.v[NL - 1] ^ lt, 0);
   }
   uint32_t rest = n.v[0] ^ 1u;  // gcd(x, q) = 1 always unless x = 0
 #pragma unroll
@@ -459,6 +462,82 @@ FP_DEV void fp_mul_inline(fp& r, const fp& a, const fp& b) {
   r = t;  // < 1.41 q for weakly reduced inputs (< 2.63 q for inputs < 4q): no final subtraction
 }
 
+// ---------------------------------------------------------------------------------------
+// Two-row Montgomery product: r = (a * x + b * y) / R mod q with ONE reduction -- the lazily
+// reduced form of an Fq2 coefficient (c0 = a0 b0 + (2q - a1) b1, c1 = a1 b0 + a0 b1,
+// fields_t.py:157-161 computes the same four products and reduces each).  Per round both product
+// rows and the reduction row go into the same even / odd column sets: 36 limb products + m.
+// 444 limb products per coefficient, 888 per Fq2 product (Karatsuba: 900 + the operand sums),
+// and the two coefficients share nothing -- the paired kernel gives one to each thread of a pair.
+//
+// Bounds: a, b <= 2q (weakly reduced, or 2q - value), x, y < 2q: the running value stays below
+// 2^32 (a + b + q) < 2^416 (5q = 0.51 R), the result below 8 q^2 / R + q = 1.82 q: weakly reduced
+// without a final subtraction.
+// ---------------------------------------------------------------------------------------
+FP_DEV void mont_round2_first(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t xi, const uint32_t* b,
+                              uint32_t yi) {
+#pragma unroll
+  for (int j = 0; j < NL; j += 2) {
+    ev[j] = mul_lo(a[j], xi);
+    ev[j + 1] = mul_hi(a[j], xi);
+    od[j] = mul_lo(a[j + 1], xi);
+    od[j + 1] = mul_hi(a[j + 1], xi);
+  }
+  mad_row<false>(od, b + 1, yi);  // no carry out of the odd set: T < 2^(32*13)
+  mad_row<false>(ev, b, yi);
+  od[NL - 1] = addc(od[NL - 1], 0);
+  uint32_t m = mul_lo(ev[0], Q_INV_NEG);
+  mad_row_q<1>(od, m);
+  mad_row_q<0>(ev, m);
+  od[NL - 1] = addc(od[NL - 1], 0);
+}
+
+FP_DEV void mont_round2(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t xi, const uint32_t* b, uint32_t yi) {
+  ev[0] = add_cc(ev[0], od[1]);
+  madc_row_rshift(od, a + 1, xi);
+  mad_row<false>(ev, a, xi);
+  od[NL - 1] = addc(od[NL - 1], 0);
+  mad_row<false>(od, b + 1, yi);
+  mad_row<false>(ev, b, yi);
+  od[NL - 1] = addc(od[NL - 1], 0);
+  uint32_t m = mul_lo(ev[0], Q_INV_NEG);
+  mad_row_q<1>(od, m);
+  mad_row_q<0>(ev, m);
+  od[NL - 1] = addc(od[NL - 1], 0);
+}
+
+// the last step of either product: T / 2^32 = ev + (od >> one word) after an even number of rounds
+FP_DEV void mont_finish(fp& r, const uint32_t* ev, const uint32_t* od) {
+  r.v[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) r.v[i] = addc_cc(ev[i], od[i + 1]);
+  r.v[NL - 1] = addc(ev[NL - 1], 0);
+}
+
+// x, y arrive four words at a time (the streaming form: the kernel loads one 16-byte chunk of each
+// per four rounds, so only a and b are held in registers for the whole product)
+struct Mul2State {
+  uint32_t ev[NL], od[NL];
+};
+template <int K>
+FP_DEV void fp_mul2_chunk(Mul2State& s, const fp& a, const fp& b, const uint32_t* x4, const uint32_t* y4) {
+  if (K == 0)
+    mont_round2_first(s.ev, s.od, a.v, x4[0], b.v, y4[0]);
+  else
+    mont_round2(s.ev, s.od, a.v, x4[0], b.v, y4[0]);
+  mont_round2(s.od, s.ev, a.v, x4[1], b.v, y4[1]);
+  mont_round2(s.ev, s.od, a.v, x4[2], b.v, y4[2]);
+  mont_round2(s.od, s.ev, a.v, x4[3], b.v, y4[3]);
+}
+
+FP_DEV void fp_mul2_inline(fp& r, const fp& a, const fp& x, const fp& b, const fp& y) {
+  Mul2State s;
+  fp_mul2_chunk<0>(s, a, b, x.v, y.v);
+  fp_mul2_chunk<1>(s, a, b, x.v + 4, y.v + 4);
+  fp_mul2_chunk<2>(s, a, b, x.v + 8, y.v + 8);
+  mont_finish(r, s.ev, s.od);
+}
+
 #if defined(B200BLS_HOSTSIM) || !defined(B200BLS_MUL_CALL)
 FP_DEV void fp_mul(fp& r, const fp& a, const fp& b) { fp_mul_inline(r, a, b); }
 #else
@@ -535,25 +614,34 @@ fp fp_inv(fp x) {
     for (int i = NL - 1; i > 0; i--) rn.v[i] = fp_funnel_l(rn.v[i - 1], rn.v[i], z);
     rn.v[0] <<= z;
     k += z;
-    // a, n odd: (a, n) <- (|a - n|, min(a, n)); the cofactor of the difference is ra + rn either way
-    fp d;
-    d.v[0] = sub_cc(a.v[0], n.v[0]);
+    // a, n odd: (a, n) <- (|a - n|, min(a, n)); the cofactor of the difference is ra + rn either way.
+    // Everything in place -- four 12-limb values of state and no 12-limb temporary: with the caller's live
+    // registers this has to fit the paired kernel's 80-register budget.
+    a.v[0] = sub_cc(a.v[0], n.v[0]);
 #pragma unroll
-    for (int i = 1; i < NL; i++) d.v[i] = subc_cc(a.v[i], n.v[i]);
+    for (int i = 1; i < NL; i++) a.v[i] = subc_cc(a.v[i], n.v[i]);
     const uint32_t lt = subc(0, 0);  // all ones when a < n
     swaps ^= lt;
-    fp s;
-    fp_add_raw(s, ra, rn);
+    n.v[0] = add_cc(n.v[0], a.v[0] & lt);  // n + (a - n) = the old a
 #pragma unroll
-    for (int i = 0; i < NL; i++) {
-      n.v[i] = lt ? a.v[i] : n.v[i];
-      rn.v[i] = lt ? ra.v[i] : rn.v[i];
+    for (int i = 1; i < NL - 1; i++) n.v[i] = addc_cc(n.v[i], a.v[i] & lt);
+    n.v[NL - 1] = addc(n.v[NL - 1], a.v[NL - 1] & lt);
+    a.v[0] = add_cc(a.v[0] ^ lt, lt & 1u);
+#pragma unroll
+    for (int i = 1; i < NL - 1; i++) a.v[i] = addc_cc(a.v[i] ^ lt, 0);
+    a.v[NL - 1] = addc(a.v[NL - 1] ^ lt, 0);
+    fp_add_raw(ra, ra, rn);
+    {  // rn <- a < n ? the old ra = (ra + rn) - rn : rn
+      uint32_t t = sub_cc(ra.v[0], rn.v[0]);
+      rn.v[0] = lt ? t : rn.v[0];
+#pragma unroll
+      for (int i = 1; i < NL - 1; i++) {
+        t = subc_cc(ra.v[i], rn.v[i]);
+        rn.v[i] = lt ? t : rn.v[i];
+      }
+      t = subc(ra.v[NL - 1], rn.v[NL - 1]);
+      rn.v[NL - 1] = lt ? t : rn.v[NL - 1];
     }
-    ra = s;
-    a.v[0] = add_cc(d.v[0] ^ lt, lt & 1u);
-#pragma unroll
-    for (int i = 1; i < NL - 1; i++) a.v[i] = addc_cc(d.v[i] ^ lt, 0);
-    a.v[NL - 1] = addc(d.v[NL - 1] ^ lt, 0);
   }
   // 1 / x == sn * rn * 2^-k with sn = -1 initially and negated by every swap
   fp r0;

@@ -42,6 +42,10 @@ struct VmParams {
   // (inactive once k reaches the segment length); prologue / epilogue address record t.
   const unsigned* seg_start;  // n_items + 1 offsets into seg_idx, or nullptr (normal mode)
   const unsigned* seg_idx;
+  // paired kernel (vm_kernel2.cuh): item blocks of 16 handed out per warp (programs without
+  // cross-thread reads), by at most active_warps warps of every CTA
+  int warp_fetch;
+  int active_warps;
   VmBuf bufs[VM_MAX_BUFS];
 };
 
