@@ -52,7 +52,8 @@ int b200bls_sync(void);                  /* wait for the library stream */
 /* The library owns 8 CUDA streams.  *_dev and *_async entry points enqueue on the stream
  * selected here (default 0); launches on different streams overlap, which removes the tail-wave
  * loss between back-to-back batches.  b200bls_sync() waits for all of them; the timer brackets
- * all of them.  Synchronous host-buffer entry points run on the selected stream. */
+ * all of them.  Synchronous host-buffer entry points run on the selected stream.  The selection is per
+ * calling thread (thread-local): host threads driving different streams do not interfere. */
 int b200bls_set_stream(int idx);
 int b200bls_stream_count(void);
 /* Launch shape = CTAs of 128 threads per SM: 1 (18 shared + 21 Tensor-Memory Fq2 workspace slots
@@ -103,6 +104,18 @@ int b200bls_field_op_batch(int level, int op, const uint8_t* a, const uint8_t* b
                            uint8_t* out, size_t n);
 int b200bls_field_op_batch_dev(int level, int op, const void* a, const void* b, void* out,
                                size_t n);
+
+/* x -> x^(q^i): fq2_qi_pow / fq6_qi_pow / fq12_qi_pow (fields_t.py:104-110, 203-212, 355-364, coefficient table
+ * 1133-1216; pinned by tests.py:60-68).  level in {2, 6, 12}, 0 <= i < level.  a, out: n x (48 * level). */
+int b200bls_field_frob_batch(int level, int i, const uint8_t* a, uint8_t* out, size_t n);
+/* x -> x^e: fq_pow / fq2_pow / fq6_pow / fq12_pow (fields_t.py:58-68, 92-101, 344-352).  level in {1, 2, 6, 12};
+ * e48: n exponents of 48 big-endian bytes (0 <= e < 2^384; e = 0 gives one). */
+int b200bls_field_pow_batch(int level, const uint8_t* a, const uint8_t* e48, uint8_t* out, size_t n);
+/* Fq.modsqrt (fields.py:199-205) / Fq2.modsqrt (fields.py:463-482, "complex method"): the reference's own root,
+ * bit for bit.  level in {1, 2}.  ok[i] = 0 (and a zero root) where the reference raises
+ * ValueError('No sqrt exists').  An Fq2 element with c1 = 0 goes through the Fq root as in the reference
+ * (which then returns an Fq object): the root is in c0, c1 = 0. */
+int b200bls_field_sqrt_batch(int level, const uint8_t* a, uint8_t* out, uint8_t* ok, size_t n);
 
 /* ---- pairing ------------------------------------------------------------------------------
  * P: n x 96 (G1 affine), Q: n x 192 (G2 affine). */
@@ -175,7 +188,19 @@ int b200bls_g2_decompress_batch(const uint8_t* in, uint8_t* out, uint8_t* ok, si
 int b200bls_g1_compress_batch(const uint8_t* in, uint8_t* out, size_t n);
 int b200bls_g2_compress_batch(const uint8_t* in, uint8_t* out, size_t n);
 
+/* fq2_untwist (fields_t.py:936-943; ec.py:402-418 untwist): points of the twist E'(Fq2), 192 bytes, ->
+ * (x / w^2, y / w^3) on E(Fq12): x' || y', 2 x 576 bytes. */
+int b200bls_g2_untwist_batch(const uint8_t* pts, uint8_t* out, size_t n);
+/* fq12_twist (fields_t.py:1018-1031; ec.py:421-437 twist): (x, y) with Fq12 coordinates, 2 x 576 bytes, ->
+ * (x w^2, y w^3), 2 x 576 bytes. */
+int b200bls_fq12_twist_batch(const uint8_t* pts, uint8_t* out, size_t n);
+/* psi (ec.py:440-444: twist(Frobenius(untwist(P)))) on affine points of the twist, 192 -> 192 bytes. */
+int b200bls_g2_psi_batch(const uint8_t* pts, uint8_t* out, size_t n);
+
 /* ---- hashing and verification ------------------------------------------------------------------ */
+/* sw_encode for Fq2 (ec.py:449-507), the Shallue-van de Woestijne map both halves of hash_to_point_Fq2 go
+ * through: t (Fq2, 96 bytes) -> affine point of the twist (192 bytes; t = 0 -> infinity = zero bytes). */
+int b200bls_sw_encode_g2_batch(const uint8_t* t, uint8_t* out, size_t n);
 /* hash_to_point_prehashed_Fq2 (ec.py:528-550): n x 32-byte message hashes -> n x 192 bytes. */
 int b200bls_hash_to_g2_batch(const uint8_t* hashes, uint8_t* out, size_t n);
 int b200bls_hash_to_g2_batch_dev(const void* hashes, void* out, size_t n);

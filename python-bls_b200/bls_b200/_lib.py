@@ -45,6 +45,13 @@ def _load():
         "b200bls_program_info": (i32, [c.c_char_p, c.POINTER(i32), c.POINTER(i32), c.POINTER(i32)]),
         "b200bls_field_op_batch": (i32, [i32, i32, vp, vp, vp, sz]),
         "b200bls_field_op_batch_dev": (i32, [i32, i32, vp, vp, vp, sz]),
+        "b200bls_field_frob_batch": (i32, [i32, i32, vp, vp, sz]),
+        "b200bls_field_pow_batch": (i32, [i32, vp, vp, vp, sz]),
+        "b200bls_field_sqrt_batch": (i32, [i32, vp, vp, vp, sz]),
+        "b200bls_sw_encode_g2_batch": (i32, [vp, vp, sz]),
+        "b200bls_g2_untwist_batch": (i32, [vp, vp, sz]),
+        "b200bls_fq12_twist_batch": (i32, [vp, vp, sz]),
+        "b200bls_g2_psi_batch": (i32, [vp, vp, sz]),
         "b200bls_pairing_batch": (i32, [vp, vp, vp, sz]),
         "b200bls_pairing_batch_async": (i32, [vp, vp, vp, sz]),
         "b200bls_pairing_batch_dev": (i32, [vp, vp, vp, sz]),

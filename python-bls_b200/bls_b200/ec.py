@@ -117,6 +117,24 @@ def infinity(g2):
     return Point(bytes(192 if g2 else 96), g2)
 
 
+def _canonical_encoding(data, raw, g2):
+    """the bytes serialize() gives back for the point `raw` decoded from `data` -- `data` itself with its two
+    spare flag bits cleared -- when `data` is the canonical encoding; None (serialize() then asks the device)
+    when it is not: an x coefficient >= q (the device reduces it on load, like Fq(Q, int)), or the sign flag on
+    a point whose sign coordinate is zero (lex_gt_neg is False there, ec.py:94-101).  Keys and signatures
+    compare, hash and sort by these bytes, so two encodings of one point must not yield two values."""
+    masked = bytes([data[0] & 0x9f]) + data[1:]
+    xs = [int.from_bytes(bytes([masked[0] & 0x1f]) + masked[1:48], "big")]
+    if g2:
+        xs.append(int.from_bytes(masked[48:96], "big"))
+    if any(x >= Q for x in xs):
+        return None
+    sign_coord = raw[144:192] if g2 else raw[48:96]         # y.c1 for the twist, y for E(Fq)
+    if (masked[0] & 0x80) and not any(sign_coord):
+        return None
+    return masked
+
+
 def point_from_bytes(data, g2):
     """PublicKey.from_bytes / Signature.from_bytes decoding (keys.py:29-40, signature.py:22-38);
     raises ValueError where the reference does"""
@@ -124,7 +142,7 @@ def point_from_bytes(data, g2):
     if not ok[0]:
         raise ValueError("No y for point x")
     p = Point(out.tobytes(), g2)
-    p._ser = bytes([data[0] & 0x9f]) + bytes(data[1:])   # what serialize() gives back (spare bits masked)
+    p._ser = _canonical_encoding(bytes(data), p.raw, g2)
     return p
 
 
@@ -145,7 +163,7 @@ def points_from_bytes(buffers, g2):
     pts = []
     for i, b in enumerate(buffers):
         p = Point(raw[w * i:w * (i + 1)], g2)
-        p._ser = bytes([b[0] & 0x9f]) + b[1:]
+        p._ser = _canonical_encoding(b, p.raw, g2)
         pts.append(p)
     return pts
 
@@ -199,6 +217,7 @@ def scalar_mul_many(points, scalars, g2):
     if not points:
         return []
     w = 192 if g2 else 96
-    sc = b"".join((int(k) % (1 << 256) if int(k) >= 0 else int(k) % N).to_bytes(32, "big") for k in scalars)
+    # the same rule as Point.__mul__: scalars outside [0, 2^256) are reduced mod the group order
+    sc = b"".join((int(k) % N if (int(k) < 0 or int(k) >> 256) else int(k)).to_bytes(32, "big") for k in scalars)
     out = engine.scalar_mul(b"".join(p.raw for p in points), sc, g2).tobytes()
     return [Point(out[w * i:w * (i + 1)], g2) for i in range(len(points))]

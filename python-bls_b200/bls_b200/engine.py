@@ -29,6 +29,80 @@ def field_op(level, op, a, b=None):
     return out
 
 
+def field_frob(level, i, a):
+    """x -> x^(q^i) for n elements of tower level 2 / 6 / 12 (qi_pow, fields_t.py:104-110, 203-212, 355-364)"""
+    _lib.init()
+    a = as_u8(a)
+    w = 48 * level
+    n = a.size // w
+    if a.size != n * w:
+        raise ValueError("operand size is not a multiple of %d" % w)
+    out = np.empty(n * w, dtype=np.uint8)
+    check(lib.b200bls_field_frob_batch(level, i, ptr(a), ptr(out), n))
+    return out
+
+
+def field_pow(level, a, exponents):
+    """x_k -> x_k^(e_k): exponents is a list of non-negative ints < 2^384, or n x 48 big-endian bytes"""
+    _lib.init()
+    a = as_u8(a)
+    w = 48 * level
+    n = a.size // w
+    if a.size != n * w:
+        raise ValueError("operand size is not a multiple of %d" % w)
+    if not isinstance(exponents, (bytes, bytearray, np.ndarray)):
+        exponents = b"".join(int(e).to_bytes(48, "big") for e in exponents)
+    e = as_u8(exponents, 48 * n)
+    out = np.empty(n * w, dtype=np.uint8)
+    check(lib.b200bls_field_pow_batch(level, ptr(a), ptr(e), ptr(out), n))
+    return out
+
+
+def field_sqrt(level, a):
+    """the reference's modsqrt on n elements of Fq (level 1) or Fq2 (level 2) -> (roots, ok flags)"""
+    _lib.init()
+    a = as_u8(a)
+    w = 48 * level
+    n = a.size // w
+    if a.size != n * w:
+        raise ValueError("operand size is not a multiple of %d" % w)
+    out = np.empty(n * w, dtype=np.uint8)
+    ok = np.empty(n, dtype=np.uint8)
+    check(lib.b200bls_field_sqrt_batch(level, ptr(a), ptr(out), ptr(ok), n))
+    return out, ok
+
+
+def _map(fn, data, w_in, w_out):
+    _lib.init()
+    data = as_u8(data)
+    n = data.size // w_in
+    if data.size != n * w_in:
+        raise ValueError("buffer size is not a multiple of %d" % w_in)
+    out = np.empty(n * w_out, dtype=np.uint8)
+    check(fn(ptr(data), ptr(out), n))
+    return out
+
+
+def sw_encode_g2(t):
+    """n x 96-byte Fq2 values -> n affine points of the twist (ec.py:449-507; infinity = zero bytes)"""
+    return _map(lib.b200bls_sw_encode_g2_batch, t, 96, 192)
+
+
+def g2_untwist(points):
+    """n affine twist points (192 B) -> n x (x', y') over Fq12 (2 x 576 B): fq2_untwist, fields_t.py:936-943"""
+    return _map(lib.b200bls_g2_untwist_batch, points, 192, 1152)
+
+
+def fq12_twist(points):
+    """n x (x, y) over Fq12 -> n x (x w^2, y w^3): fq12_twist, fields_t.py:1018-1031"""
+    return _map(lib.b200bls_fq12_twist_batch, points, 1152, 1152)
+
+
+def g2_psi(points):
+    """psi = twist . Frobenius . untwist on n affine twist points (ec.py:440-444)"""
+    return _map(lib.b200bls_g2_psi_batch, points, 192, 192)
+
+
 def _pq(P, Q):
     P, Q = as_u8(P), as_u8(Q)
     n = P.size // 96
@@ -68,7 +142,7 @@ def miller_product(P, Q):
     _lib.init()
     P, Q, n = _pq(P, Q)
     out = np.empty(576, dtype=np.uint8)
-    check(lib.b200bls_miller_product(ptr(P), ptr(Q), ptr(out), n))
+    check(lib.b200bls_miller_product(ptr(P) if n else None, ptr(Q) if n else None, ptr(out), n))
     return out
 
 
@@ -77,7 +151,7 @@ def pairing_multi(P, Q):
     _lib.init()
     P, Q, n = _pq(P, Q)
     out = np.empty(576, dtype=np.uint8)
-    check(lib.b200bls_pairing_multi(ptr(P), ptr(Q), ptr(out), n))
+    check(lib.b200bls_pairing_multi(ptr(P) if n else None, ptr(Q) if n else None, ptr(out), n))
     return out
 
 

@@ -387,20 +387,23 @@ def build_miller_raw():
 def build_miller_hash_raw():
     """stage 1 of aggregate verification: H = hash_to_g2(message hash) and the Miller loop of
     (P, H) in one program, H projective (no inversion).  buffers: 0 = P (n x 96), 1 = SHA stage
-    output (n x 256), 2 = raw SoA Fq12 per item, 3 = an explicitly given affine Q per item (n x 192):
-    where it is not all-zero it replaces the hashed point -- that is how the e(-G1, signature)
-    pair rides in the same launch as the n (pk, H(m)) pairs."""
+    output (n x 256), 2 = raw SoA Fq12 per item, 3 = an explicitly given affine Q per item (n x 192),
+    4 = one byte per item: non-zero where buffer 3 replaces the hashed point -- that is how the
+    e(-G1, signature) pair rides in the same launch as the n (pk, H(m)) pairs.  The flag is explicit
+    because all-zero bytes are a legitimate given Q: the point at infinity (an aggregate signature that
+    sums to infinity), which contributes the factor 1 like everywhere else."""
     from .hashg2 import hash_to_g2
     prog = Program("miller_hash_raw")
     prog.begin_body()
     hx, hy, hz = hash_to_g2(prog, 1, affine=False)
     hz2 = hz.sqr()
     xg, yg = load_g2(prog, 3)
-    given = ~(xg.is_zero() & yg.is_zero())
+    given = prog.flag_byte(4, 0)
+    given_inf = given & xg.is_zero() & yg.is_zero()
     one = prog.const2((1, 0))
     hq = (prog.sel2(given, xg, hx * hz), prog.sel2(given, yg, hy), prog.sel2(given, one, hz2 * hz))
     xk, yk = load_g1(prog, 0)
-    inf = (xk.is_zero() & yk.is_zero()) | hq[2].is_zero()
+    inf = (xk.is_zero() & yk.is_zero()) | hq[2].is_zero() | given_inf
     f = miller_loop_multi(prog, [(xk, yk, hq, None, inf)])
     for k, c in enumerate(f.coeffs()):
         prog.store_raw2(2, k, c)

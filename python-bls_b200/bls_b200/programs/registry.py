@@ -1,7 +1,7 @@
 """Name -> builder table of every VM program embedded into libb200bls.so."""
 import os
 
-from . import curve, fieldops, hashg2, pairing
+from . import curve, extras, fieldops, hashg2, pairing
 
 # Launch shapes: CTAs (of 128 threads) per SM -> (Fq2 slots per thread in shared memory, slots in
 # Tensor Memory).  Shared memory: ctas * slots * 96 B * 128 <= 227 KB; TMEM: ctas * pow2(24 *
@@ -34,6 +34,20 @@ PROGRAMS["miller_hash_raw"] = pairing.build_miller_hash_raw
 PROGRAMS["f12_prod1"] = pairing.build_f12_product_pass1
 PROGRAMS["f12_prod2"] = pairing.build_f12_product_pass2
 PROGRAMS["hash_to_g2"] = hashg2.build_hash_to_g2
+# single-function parity programs (golden-vector replay of reference functions the hot programs only use inside
+# larger computations); pow is 384 square-and-multiply steps: assembled for the one-CTA-per-SM shape only
+PROGRAMS["sw_encode_g2"] = extras.build_sw_encode
+for _level in (2, 6, 12):
+    for _i in range(_level):
+        PROGRAMS["f%d_frob%d" % (_level, _i)] = extras.build_frob(_level, _i)
+for _level in (1, 2, 6, 12):
+    PROGRAMS["f%d_pow" % _level] = extras.build_pow(_level)
+for _level in (1, 2):
+    PROGRAMS["f%d_sqrt" % _level] = extras.build_sqrt(_level)
+PROGRAMS["g2_untwist"] = extras.build_untwist
+PROGRAMS["f12_twist"] = extras.build_twist12
+PROGRAMS["g2_psi"] = extras.build_psi
+SHAPE1_ONLY = {"f1_pow", "f2_pow", "f6_pow", "f12_pow"} | {n for n in PROGRAMS if "_frob" in n}
 for _g2 in (False, True):
     _p = "g2" if _g2 else "g1"
     PROGRAMS[_p + "_mul"] = curve.build_scalar_mul(_g2)

@@ -328,9 +328,10 @@ class Program:
         self.emit("FSET", f, int(bit))
         return f
 
-    def flag_bit(self, buf, bit):
+    def flag_bit(self, buf, bit, nbytes=32):
+        """bit `bit` of the item's big-endian scalar of `nbytes` bytes in buffer `buf`"""
         f = Flag(self)
-        self.emit("FBIT", f, buf, bit)
+        self.emit("FBIT", f, buf, bit, aux=(nbytes - 1 if nbytes != 32 else None))
         return f
 
     def flag_byte(self, buf, off):

@@ -44,7 +44,7 @@ OPS = [
     ("FXOR", "f f f", ""),
     ("FNOT", "f f -", ""),
     ("FSET", "f i -", "flag[d] = a & 1"),
-    ("FBIT", "f u i", "flag[d] = bit b of the item's 32-byte big-endian scalar in buffer a"),
+    ("FBIT", "f u i", "flag[d] = bit b of the item's big-endian scalar in buffer a (aux + 1 bytes; aux = 0: 32 bytes)"),
     ("FACTIVE", "f - -", "flag[d] = item index < n_items"),
     ("CSEL2", "c2 c2 c2", "d = flag[aux] ? a : b"),
     ("CSEL1", "c1 c1 c1", ""),

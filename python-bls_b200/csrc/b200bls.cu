@@ -92,7 +92,6 @@ struct Context {
   int device = -1;
   int sm_count = 0;
   StreamCtx sc[N_STREAMS];
-  int cur = 0;               // stream used by the calling API function (b200bls_set_stream)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::map<std::string, DevProgram> programs;
   uint64_t launches = 0;
@@ -102,8 +101,11 @@ struct Context {
 
 Context g_ctx;
 std::mutex g_mu;
+// stream used by the calling THREAD's API calls (b200bls_set_stream): host threads that drive different
+// library streams do not disturb each other's selection
+thread_local int t_stream = 0;
 
-StreamCtx& cur() { return g_ctx.sc[g_ctx.cur]; }
+StreamCtx& cur() { return g_ctx.sc[t_stream]; }
 #define STREAM (cur().stream)
 
 int ensure_buf(Staging& s, size_t bytes);
@@ -603,7 +605,13 @@ int raw_product_dev(void* out576, size_t n) {
 
 int miller_product_dev(const void* P, const void* Q, void* out576, size_t n) {
   NEED_READY();
-  if (n == 0) return fail(B200BLS_E_ARG, "pairing_multi needs at least one pair");
+  if (n == 0) {  // the empty product (fields_t.py:1117: prod starts at one)
+    static const uint8_t kOne[48] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
+    CU(cudaMemsetAsync(out576, 0, 576, STREAM));
+    CU(cudaMemcpyAsync(out576, kOne, 48, cudaMemcpyHostToDevice, STREAM));
+    return 0;
+  }
   int rc = ensure_scratch(1, (size_t)576 * n);
   if (rc) return rc;
   VmBuf ba[3] = {vb(P, 96), vb(Q, 192), vb(cur().scratch[1].ptr, (long long)n)};
@@ -617,16 +625,17 @@ int sha_stage_dev(const void* hashes, void* out256, size_t n);
 // Miller product of aggregate verification over m = n + 1 items in ONE launch: item 0 is the pair
 // (-G1, signature), given explicitly in Qgiven; items 1..n are (pk_i, H(mh_i)), hashed and paired
 // in the same program with H projective.  P: m x 96, mh: m x 32 (item 0 unused), Qgiven: m x 192
-// (zero where the hashed point is to be used).
-int aggregate_miller_dev(const void* P, const void* mh, const void* Qgiven, void* out576, size_t m) {
+// (used where given[i] != 0), given: m bytes.
+int aggregate_miller_dev(const void* P, const void* mh, const void* Qgiven, const void* given, void* out576, size_t m) {
   NEED_READY();
   int rc = ensure_scratch(1, (size_t)576 * m);
   if (!rc) rc = ensure_scratch(3, (size_t)256 * m);
   if (rc) return rc;
   rc = sha_stage_dev(mh, cur().scratch[3].ptr, m);
   if (rc) return rc;
-  VmBuf bb[4] = {vb(P, 96), vb(cur().scratch[3].ptr, 256), vb(cur().scratch[1].ptr, (long long)m), vb(Qgiven, 192)};
-  rc = launch_named("miller_hash_raw", m, bb, 4);
+  VmBuf bb[5] = {vb(P, 96), vb(cur().scratch[3].ptr, 256), vb(cur().scratch[1].ptr, (long long)m), vb(Qgiven, 192),
+                 vb(given, 1)};
+  rc = launch_named("miller_hash_raw", m, bb, 5);
   if (rc) return rc;
   return raw_product_dev(out576, m);
 }
@@ -802,7 +811,6 @@ int b200bls_init(int device) {
     CU(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming));
     CU(cudaMalloc(&sc.counters, N_COUNTERS * sizeof(int)));
   }
-  c.cur = 0;
   CU(cudaEventCreate(&c.ev0));
   CU(cudaEventCreate(&c.ev1));
   CU(cudaFuncSetAttribute(vm_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -917,15 +925,15 @@ int b200bls_set_ctas_per_sm(int n) {
 int b200bls_get_ctas_per_sm(void) { return g_ctx.ctas_per_sm; }
 
 int b200bls_sync(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
   for (auto& sc : g_ctx.sc) CU(cudaStreamSynchronize(sc.stream));
   return 0;
 }
 
 int b200bls_set_stream(int idx) {
-  std::lock_guard<std::mutex> lk(g_mu);
   if (idx < 0 || idx >= N_STREAMS) return fail(B200BLS_E_ARG, "stream index out of range (0..%d)", N_STREAMS - 1);
-  g_ctx.cur = idx;
+  t_stream = idx;   // per calling thread
   return 0;
 }
 
@@ -968,12 +976,14 @@ void b200bls_host_free(void* p) {
 }
 
 int b200bls_h2d(void* dst, const void* src, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
   CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, STREAM));
   return 0;
 }
 
 int b200bls_d2h(void* dst, const void* src, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
   CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, STREAM));
   return 0;
@@ -982,6 +992,7 @@ int b200bls_d2h(void* dst, const void* src, size_t bytes) {
 // The timed region covers ALL library streams: every stream waits for the start event, and
 // the stop event is recorded on stream 0 after it has waited for the work of every other one.
 int b200bls_timer_start(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
   CU(cudaEventRecord(g_ctx.ev0, g_ctx.sc[0].stream));
   for (int i = 1; i < N_STREAMS; i++) CU(cudaStreamWaitEvent(g_ctx.sc[i].stream, g_ctx.ev0, 0));
@@ -989,6 +1000,7 @@ int b200bls_timer_start(void) {
 }
 
 int b200bls_timer_stop(float* ms) {
+  std::lock_guard<std::mutex> lk(g_mu);
   if (!g_ctx.ready) return fail(B200BLS_E_NOT_INIT, "not initialised");
   for (int i = 1; i < N_STREAMS; i++) {
     CU(cudaEventRecord(g_ctx.sc[i].done, g_ctx.sc[i].stream));
@@ -1043,6 +1055,67 @@ int b200bls_field_op_batch_dev(int level, int op, const void* a, const void* b, 
   size_t w = 48 * (size_t)level;
   DevBuf db[3] = {{a, w}, {b ? b : a, w}, {out, w}};
   return run_dev(name, n, db, 3);
+}
+
+// ---- single-function parity entry points (programs/extras.py) ------------------------------------------
+int b200bls_field_frob_batch(int level, int i, const uint8_t* a, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!(level == 2 || level == 6 || level == 12) || i < 0 || i >= level)
+    return fail(B200BLS_E_ARG, "field_frob: level %d, power %d (want level 2, 6 or 12 and 0 <= i < level)", level, i);
+  if (!a || !out) return fail(B200BLS_E_ARG, "null buffer");
+  char name[32];
+  snprintf(name, sizeof(name), "f%d_frob%d", level, i);
+  const size_t w = 48 * (size_t)level;
+  HostBuf hb[2] = {{a, nullptr, w}, {nullptr, out, w}};
+  return run_host(name, n, hb, 2);
+}
+
+int b200bls_field_pow_batch(int level, const uint8_t* a, const uint8_t* e48, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!(level == 1 || level == 2 || level == 6 || level == 12)) return fail(B200BLS_E_ARG, "field_pow: bad level %d", level);
+  if (!a || !e48 || !out) return fail(B200BLS_E_ARG, "null buffer");
+  char name[32];
+  snprintf(name, sizeof(name), "f%d_pow", level);
+  const size_t w = 48 * (size_t)level;
+  HostBuf hb[3] = {{a, nullptr, w}, {e48, nullptr, 48}, {nullptr, out, w}};
+  return run_host(name, n, hb, 3);
+}
+
+int b200bls_field_sqrt_batch(int level, const uint8_t* a, uint8_t* out, uint8_t* ok, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!(level == 1 || level == 2)) return fail(B200BLS_E_ARG, "field_sqrt: level %d (want 1 or 2)", level);
+  if (!a || !out || !ok) return fail(B200BLS_E_ARG, "null buffer");
+  const size_t w = 48 * (size_t)level;
+  HostBuf hb[3] = {{a, nullptr, w}, {nullptr, out, w}, {nullptr, ok, 1}};
+  return run_host(level == 1 ? "f1_sqrt" : "f2_sqrt", n, hb, 3);
+}
+
+int b200bls_sw_encode_g2_batch(const uint8_t* t, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!t || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[2] = {{t, nullptr, 96}, {nullptr, out, 192}};
+  return run_host("sw_encode_g2", n, hb, 2);
+}
+
+int b200bls_g2_untwist_batch(const uint8_t* pts, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!pts || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[2] = {{pts, nullptr, 192}, {nullptr, out, 1152}};
+  return run_host("g2_untwist", n, hb, 2);
+}
+
+int b200bls_fq12_twist_batch(const uint8_t* pts, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!pts || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[2] = {{pts, nullptr, 1152}, {nullptr, out, 1152}};
+  return run_host("f12_twist", n, hb, 2);
+}
+
+int b200bls_g2_psi_batch(const uint8_t* pts, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!pts || !out) return fail(B200BLS_E_ARG, "null buffer");
+  HostBuf hb[2] = {{pts, nullptr, 192}, {nullptr, out, 192}};
+  return run_host("g2_psi", n, hb, 2);
 }
 
 int b200bls_pairing_batch(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n) {
@@ -1217,7 +1290,7 @@ int b200bls_hash_pks_dev(const void* pk_hash32, uint32_t first_index, void* out,
 }
 int b200bls_miller_product(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (!P || !Q || !out) return fail(B200BLS_E_ARG, "null buffer");
+  if (!out || (n && (!P || !Q))) return fail(B200BLS_E_ARG, "null buffer");
   HostIO io[3] = {{P, nullptr, 96 * n}, {Q, nullptr, 192 * n}, {nullptr, out, 576}};
   return with_staging(io, 3, [&](void** d) { return miller_product_dev(d[0], d[1], d[2], n); });
 }
@@ -1227,7 +1300,7 @@ int b200bls_miller_product_dev(const void* P, const void* Q, void* out, size_t n
 }
 int b200bls_pairing_multi(const uint8_t* P, const uint8_t* Q, uint8_t* out, size_t n) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (!P || !Q || !out) return fail(B200BLS_E_ARG, "null buffer");
+  if (!out || (n && (!P || !Q))) return fail(B200BLS_E_ARG, "null buffer");
   HostIO io[4] = {{P, nullptr, 96 * n}, {Q, nullptr, 192 * n}, {nullptr, nullptr, 576}, {nullptr, out, 576}};
   return with_staging(io, 4, [&](void** d) {
     int rc = miller_product_dev(d[0], d[1], d[2], n);
@@ -1281,17 +1354,29 @@ const uint8_t kNegG1[96] = {
 // final-exponentiated) at staging[3]; sig may be null (a rank that does not own that pair)
 int aggregate_miller_host(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n) {
   const size_t lead = sig ? 1 : 0, m = n + lead;
-  if (m == 0) return fail(B200BLS_E_ARG, "aggregate Miller product needs at least one pair");
   int rc;
+  if ((rc = ensure_staging(3, 576 * 2))) return rc;
+  if (m == 0) {
+    // an empty slice (a rank of a sharded verification that owns no pair) contributes the empty product:
+    // one, so that every rank still reaches the exchange
+    static const uint8_t kOne[48] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
+    CU(cudaMemsetAsync(cur().staging[3].ptr, 0, 576, STREAM));
+    CU(cudaMemcpyAsync(cur().staging[3].ptr, kOne, 48, cudaMemcpyHostToDevice, STREAM));
+    return 0;
+  }
   if ((rc = ensure_staging(0, 96 * m))) return rc;
   if ((rc = ensure_staging(1, 32 * m))) return rc;
   if ((rc = ensure_staging(2, 192 * m))) return rc;
-  if ((rc = ensure_staging(3, 576 * 2))) return rc;
+  if ((rc = ensure_staging(4, m))) return rc;
   uint8_t* dP = (uint8_t*)cur().staging[0].ptr;
   uint8_t* dM = (uint8_t*)cur().staging[1].ptr;
   uint8_t* dQ = (uint8_t*)cur().staging[2].ptr;
+  uint8_t* dG = (uint8_t*)cur().staging[4].ptr;
   CU(cudaMemsetAsync(dQ, 0, 192 * m, STREAM));
+  CU(cudaMemsetAsync(dG, 0, m, STREAM));
   if (sig) {
+    CU(cudaMemsetAsync(dG, 1, 1, STREAM));   // item 0 is the explicitly given (-G1, signature) pair
     CU(cudaMemcpyAsync(dP, kNegG1, 96, cudaMemcpyHostToDevice, STREAM));
     CU(cudaMemcpyAsync(dQ, sig, 192, cudaMemcpyHostToDevice, STREAM));
     CU(cudaMemsetAsync(dM, 0, 32, STREAM));
@@ -1300,7 +1385,7 @@ int aggregate_miller_host(const uint8_t* sig, const uint8_t* pks, const uint8_t*
     CU(cudaMemcpyAsync(dP + 96 * lead, pks, 96 * n, cudaMemcpyHostToDevice, STREAM));
     CU(cudaMemcpyAsync(dM + 32 * lead, mhs, 32 * n, cudaMemcpyHostToDevice, STREAM));
   }
-  return aggregate_miller_dev(dP, dM, dQ, cur().staging[3].ptr, m);
+  return aggregate_miller_dev(dP, dM, dQ, dG, cur().staging[3].ptr, m);
 }
 }  // namespace
 

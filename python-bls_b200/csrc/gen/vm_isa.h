@@ -34,7 +34,7 @@ enum VmOp : int {
   OP_FXOR = 30,  // f f f
   OP_FNOT = 31,  // f f -
   OP_FSET = 32,  // f i -  flag[d] = a & 1
-  OP_FBIT = 33,  // f u i  flag[d] = bit b of the item's 32-byte big-endian scalar in buffer a
+  OP_FBIT = 33,  // f u i  flag[d] = bit b of the item's big-endian scalar in buffer a (aux + 1 bytes; aux = 0: 32 bytes)
   OP_FACTIVE = 34,  // f - -  flag[d] = item index < n_items
   OP_CSEL2 = 35,  // c2 c2 c2  d = flag[aux] ? a : b
   OP_CSEL1 = 36,  // c1 c1 c1

@@ -268,7 +268,7 @@ FP_DEV int vm_exec2(Env& env, uint32_t w0, uint32_t w1) {
       env.set_flag(d, (a & 1) != 0);
       break;
     case OP_FBIT: {
-      uint32_t byte = env.ld_byte(a, 31 - (b >> 3));
+      uint32_t byte = env.ld_byte(a, (aux ? aux : 31) - (b >> 3));  // aux = scalar bytes - 1 (0: 32-byte scalars)
       env.set_flag(d, ((byte >> (b & 7)) & 1) != 0);
     } break;
     case OP_FLDB:

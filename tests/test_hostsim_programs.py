@@ -449,3 +449,124 @@ def test_miller_squaring_and_compressed_power_against_oracle():
     for i in range(len(fs)):
         assert o1.tobytes()[576 * i:576 * (i + 1)] == ser(O.f12_scale(O.f12_mul(fs[i], fs[i]), 2)), i
         assert o2.tobytes()[576 * i:576 * (i + 1)] == ser(O.f12_pow(ms[i], pairing.X_ABS)), i
+
+
+# ---- single-function parity programs (programs/extras.py): the reference's golden vectors for functions the hot
+# programs only use inside larger computations, replayed on the device code --------------------------------------
+def _u8(b):
+    return np.frombuffer(bytes(b), dtype=np.uint8).copy()
+
+
+def test_sw_encode_program_all_golden_vectors_incl_edge_branches():
+    """ec.py:449-507 on all 29 golden vectors from the live reference, among them the branch no hash ever
+    reaches: t = 0 -> infinity (the Fq2 analogue of tests.py:104)"""
+    from bls_b200.programs import extras
+    g = load_golden("hash_kat.json")
+    cases = list(g["sw_encode"])
+    assert any(c["out"]["inf"] for c in cases)
+    # w0 = t^2 + b + 1 = 0 (-> generator, ec.py:466-470) has NO solution over Fq2: -(5 + 4u) has norm 41, a
+    # non-residue mod q, so it is not a square -- the branch exists in the reference and in the program but no
+    # input reaches it (the reference's own KATs for it, tests.py:106-107, are for the G1 map over Fq)
+    assert pow(41, (O.Q - 1) // 2, O.Q) == O.Q - 1
+    with pytest.raises(ValueError):
+        O.f2_sqrt(((-5) % O.Q, (-4) % O.Q))
+    T = _u8(b"".join(bytes.fromhex(c["t"]) for c in cases))
+    for ns, ntm in ((18, 21), (6, 7)):
+        asm = extras.build_sw_encode().assemble(ns, n_cold=4096, n_tmem=ntm)
+        out = np.full(192 * len(cases), 7, dtype=np.uint8)
+        hostsim.run(asm, {0: T, 1: out}, {0: 96, 1: 192}, len(cases), n_blocks=2, nt=4)
+        raw = out.tobytes()
+        for i, c in enumerate(cases):
+            want = bytes(192) if c["out"]["inf"] else bytes.fromhex(c["out"]["x"] + c["out"]["y"])
+            assert raw[192 * i:192 * (i + 1)] == want, (ns, i)
+
+
+def test_frobenius_pow_sqrt_programs_golden():
+    """fields_t.py:344-364 (pow, qi_pow) and fields.py:199-205, 463-482 (modsqrt): the 20 + 3 + 16 golden cases"""
+    from bls_b200.programs import extras
+    g = load_golden("field_kat.json")
+    seen = {"frob": 0, "pow": 0, "sqrt": 0}
+    for c in g["cases"]:
+        level, op = c["level"], c["op"]
+        if op not in seen:
+            continue
+        w = 48 * level
+        a = bytes.fromhex(c["a"]) if len(c["a"]) == 2 * w else None
+        if a is None:                                  # operands stored by name
+            a = b"".join(int(x).to_bytes(48, "big") for x in g["operands"][str(level)][c["a"]])
+        a = _u8(a)
+        if op == "frob":
+            asm = extras.build_frob(level, c["i"])().assemble(18, n_cold=64, n_tmem=21)
+            out = np.zeros(w, dtype=np.uint8)
+            hostsim.run(asm, {0: a, 1: out}, {0: w, 1: w}, 1, nt=2)
+            assert out.tobytes().hex() == c["out"], (level, c["i"])
+        elif op == "pow":
+            asm = extras.build_pow(level)().assemble(18, n_cold=64, n_tmem=21)
+            e = int(c["e"], 16)
+            out = np.zeros(2 * w, dtype=np.uint8)
+            # second item: exponent 0 -> one; same base
+            hostsim.run(asm, {0: np.concatenate([a, a]), 1: _u8(e.to_bytes(48, "big") + bytes(48)), 2: out},
+                        {0: w, 1: 48, 2: w}, 2, nt=2)
+            assert out.tobytes()[:w].hex() == c["out"], level
+            assert out.tobytes()[w:] == (1).to_bytes(48, "big") + bytes(w - 48)
+        else:
+            asm = extras.build_sqrt(level)().assemble(18, n_cold=64, n_tmem=21)
+            out = np.full(w, 9, dtype=np.uint8)
+            ok = np.full(1, 9, dtype=np.uint8)
+            hostsim.run(asm, {0: a, 1: out, 2: ok}, {0: w, 1: w, 2: 1}, 1, nt=2)
+            if c["out"] is None:
+                assert ok[0] == 0 and not out.any(), level
+            else:
+                assert ok[0] == 1 and out.tobytes().hex() == c["out"], level
+        seen[op] += 1
+    assert seen == {"frob": 20, "pow": 3, "sqrt": 16}
+    # Fq2.modsqrt on a real element (a1 = 0) goes through the Fq root (fields.py:467-469); zero -> zero
+    asm = extras.build_sqrt(2)().assemble(18, n_cold=64, n_tmem=21)
+    sq = pow(12345, 2, O.Q)
+    nonres = next(x for x in range(2, 50) if pow(x, (O.Q - 1) // 2, O.Q) != 1)
+    ins = [(sq, 0), (nonres, 0), (0, 0)]
+    a = _u8(b"".join(x.to_bytes(48, "big") + y.to_bytes(48, "big") for x, y in ins))
+    out = np.full(96 * 3, 9, dtype=np.uint8)
+    ok = np.full(3, 9, dtype=np.uint8)
+    hostsim.run(asm, {0: a, 1: out, 2: ok}, {0: 96, 1: 96, 2: 1}, 3, nt=4)
+    assert list(ok) == [1, 0, 1]
+    assert out.tobytes()[:96] == O.fq_sqrt(sq).to_bytes(48, "big") + bytes(48) and not out[96:].any()
+
+
+def test_twist_maps_and_psi_programs():
+    """fields_t.py:936-943, 1018-1031, ec.py:402-444 against the oracle's Fq12 arithmetic and the golden psi vectors"""
+    from bls_b200.programs import extras
+
+    def f12b(t):
+        return b"".join(int(c).to_bytes(48, "big") for c in t)
+    g = load_golden("hash_kat.json")
+    pts = [O.aff_mul(k, O.G2) for k in (1, 7, 1234567)]
+    P = _u8(b"".join(b"".join(c.to_bytes(48, "big") for c in (p[0][0], p[0][1], p[1][0], p[1][1])) for p in pts))
+    out = np.zeros(1152 * len(pts), dtype=np.uint8)
+    hostsim.run(extras.build_untwist().assemble(6, n_cold=64, n_tmem=7), {0: P, 1: out}, {0: 192, 1: 1152}, len(pts), nt=2)
+    for i, p in enumerate(pts):
+        ux, uy, _ = O.untwist((p[0], p[1], False))
+        assert out.tobytes()[1152 * i:1152 * (i + 1)] == f12b(ux) + f12b(uy), i
+    # twist of arbitrary Fq12 coordinates, and twist(untwist(P)) = P embedded
+    import random
+    rnd = random.Random(77)
+    xs = [tuple(rnd.randrange(O.Q) for _ in range(12)) for _ in range(4)]
+    inp = np.concatenate([_u8(f12b(xs[0]) + f12b(xs[1]) + f12b(xs[2]) + f12b(xs[3])), out[:1152]])
+    res = np.zeros(1152 * 3, dtype=np.uint8)
+    hostsim.run(extras.build_twist12().assemble(18, n_cold=64, n_tmem=0), {0: inp, 1: res}, {0: 1152, 1: 1152}, 3, nt=2)
+    for i in range(2):
+        tx, ty, _ = O.twist((xs[2 * i], xs[2 * i + 1], False))
+        assert res.tobytes()[1152 * i:1152 * (i + 1)] == f12b(tx) + f12b(ty), i
+    p = pts[0]
+    assert res.tobytes()[2304:] == f12b(tuple(p[0]) + (0,) * 10) + f12b(tuple(p[1]) + (0,) * 10)
+    # psi: golden vectors from the live reference + the oracle on more points
+    cases = [(bytes.fromhex(c["p"]["x"] + c["p"]["y"]), bytes.fromhex(c["out"]["x"] + c["out"]["y"])) for c in g["psi"]]
+    for p in pts[1:]:
+        q = O.psi((p[0], p[1], False))
+        cases.append((b"".join(c.to_bytes(48, "big") for c in (p[0][0], p[0][1], p[1][0], p[1][1])),
+                      b"".join(c.to_bytes(48, "big") for c in (q[0][0], q[0][1], q[1][0], q[1][1]))))
+    out = np.zeros(192 * len(cases), dtype=np.uint8)
+    hostsim.run(extras.build_psi().assemble(6, n_cold=64, n_tmem=7), {0: _u8(b"".join(c[0] for c in cases)), 1: out},
+                {0: 192, 1: 192}, len(cases), nt=4)
+    for i, c in enumerate(cases):
+        assert out.tobytes()[192 * i:192 * (i + 1)] == c[1], i

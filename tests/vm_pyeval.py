@@ -120,7 +120,7 @@ def run(prog, bufs, n_items, n_threads=1, strides=None, out_bufs=None):
                 elif nm == "FSET":
                     r = bool(op.a & 1)
                 elif nm == "FBIT":
-                    sc = rd(op.a, item, 0, 32)
+                    sc = rd(op.a, item, 0, (op.aux + 1) if op.aux else 32)
                     r = bool((sc >> op.b) & 1)
                 elif nm == "FLDB":
                     r = rd(op.a, item, op.b, 1) != 0

@@ -27,6 +27,8 @@ def main(out_path=None):
     progs = []
     for base, builder in registry.PROGRAMS.items():
         for ctas, (n_slots, n_tmem) in registry.SHAPES.items():
+            if ctas != 1 and base in getattr(registry, "SHAPE1_ONLY", ()):
+                continue
             name = "%s@%d" % (base, ctas)
             t = time.time()
             asm = None
