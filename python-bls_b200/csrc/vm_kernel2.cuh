@@ -46,31 +46,33 @@ __device__ __forceinline__ void shfl_fp(fp& x) {
 template <bool USE_TMEM, int NT>
 __device__ __forceinline__ fp fp_mul2_stream(const fp& a, const fp& b, uint32_t src) {
   Mul2State s;
-  uint32_t x4[4], y4[4];
-#define B200BLS_MUL2_LOAD(K)                                                   \
-  if (!USE_TMEM || !(src & 1u)) {                                              \
-    const uint4 xv = lds128(src + (K) * (NT * 16));                            \
-    const uint4 yv = lds128((src ^ 16u) + (K) * (NT * 16));                    \
-    x4[0] = xv.x, x4[1] = xv.y, x4[2] = xv.z, x4[3] = xv.w;                    \
-    y4[0] = yv.x, y4[1] = yv.y, y4[2] = yv.z, y4[3] = yv.w;                    \
-  } else {                                                                     \
-    uint32_t o4[4];                                                            \
-    tm_ld4((src >> 2) + 4 * (K), o4);                                          \
-    tm_wait_ld();                                                              \
-    _Pragma("unroll") for (int i = 0; i < 4; i++) {                            \
-      const uint32_t p = __shfl_xor_sync(0xffffffffu, o4[i], 1);               \
-      x4[i] = (src & 2u) ? p : o4[i];                                          \
-      y4[i] = (src & 2u) ? o4[i] : p;                                          \
-    }                                                                          \
-  }
+#pragma unroll
+  for (int i = 0; i < NL; i++) s.ev[i] = s.od[i] = 0;
   if (USE_TMEM && (src & 1u)) tm_wait_st();
-  B200BLS_MUL2_LOAD(0)
-  fp_mul2_chunk<0>(s, a, b, x4, y4);
-  B200BLS_MUL2_LOAD(1)
-  fp_mul2_chunk<1>(s, a, b, x4, y4);
-  B200BLS_MUL2_LOAD(2)
-  fp_mul2_chunk<2>(s, a, b, x4, y4);
-#undef B200BLS_MUL2_LOAD
+  // three passes of four rounds: a loop, not 12 unrolled rounds -- the hot code has to fit the instruction cache
+#pragma unroll 1
+  for (int k = 0; k < 3; k++) {
+    uint32_t x4[4], y4[4];
+    if (!USE_TMEM || !(src & 1u)) {
+      const uint4 xv = lds128(src);
+      const uint4 yv = lds128(src ^ 16u);
+      x4[0] = xv.x, x4[1] = xv.y, x4[2] = xv.z, x4[3] = xv.w;
+      y4[0] = yv.x, y4[1] = yv.y, y4[2] = yv.z, y4[3] = yv.w;
+      src += NT * 16;
+    } else {
+      uint32_t o4[4];
+      tm_ld4(src >> 2, o4);
+      tm_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t p = __shfl_xor_sync(0xffffffffu, o4[i], 1);
+        x4[i] = (src & 2u) ? p : o4[i];
+        y4[i] = (src & 2u) ? o4[i] : p;
+      }
+      src += 4u << 2;
+    }
+    fp_mul2_rounds4(s, a, b, x4, y4);
+  }
   fp r;
   mont_finish(r, s.ev, s.od);
   return r;
@@ -288,20 +290,6 @@ struct PairEnv {
 // Runs one program section, from `lo` to its END instruction.  The next instruction word is loaded
 // before the current one executes and consumed (through a volatile move) after it; one L1 line holds
 // 16 instructions and the line after next is prefetched at every line boundary.
-template <class Env>
-__device__ __forceinline__ void vm2_run_section(Env& env, const uint2* pc) {
-  // the program counter is the instruction pointer itself (program images are 256-byte aligned)
-  for (;;) {
-#ifdef B200BLS_VM2_PREFETCH_INS
-    if (((uint32_t)(uintptr_t)pc & 127u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(pc + 32));
-#endif
-    const uint2 ins = __ldg(pc);
-    const int skip = vm_exec2(env, ins.x, ins.y);
-    if (skip < 0) break;
-    pc += 1 + skip;
-  }
-}
-
 // USE_TMEM = false: no tcgen05 instruction in the kernel at all (a kernel that merely contains
 // tcgen05.alloc holds the SM's allocation permit until it relinquishes it, vm_kernel.cuh).
 // SEG: segmented launch mode (multi-scalar multiplication buckets, see VmParams); its per-thread
@@ -361,49 +349,49 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) vm2_kernel(const __grid_constant
   // per-warp item blocks: warps beyond the launcher's bound do not take part in the item loop
   const bool warp_mode = p.warp_fetch != 0;
   const bool warp_idle = warp_mode && (int)(threadIdx.x >> 5) >= p.active_warps;
-  for (int phase = warp_idle ? 3 : 0; phase < 3;) {
-    int lo;
-    if (phase == 0) {
-      lo = 0;
-      phase = 1;
-    } else if (phase == 1 && seg_mode) {
-      if (seg_k >= seg_iters) {
-        phase = 2;
+  // One interpreter loop serves the three sections.  Which section an END instruction closes is read
+  // off the program counter, so no section state lives in a register across the instruction bodies:
+  // after the prologue and after every body pass the next item block is fetched (body again, or on to
+  // the epilogue when the batch is exhausted); the END of the epilogue leaves the loop.
+  const uint2* pc = p.code;
+  while (!warp_idle) {
+#ifdef B200BLS_VM2_PREFETCH_INS
+    if (((uint32_t)(uintptr_t)pc & 127u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(pc + 32));
+#endif
+    const uint2 ins = __ldg(pc);
+    const int skip = vm_exec2(env, ins.x, ins.y);
+    if (skip >= 0) {
+      pc += 1 + skip;
+      continue;
+    }
+    if (pc - p.code >= p.epi_start) break;  // END of the epilogue
+    bool more;
+    if (seg_mode) {
+      more = seg_k < seg_iters;
+      if (more) {
+        const bool act = seg_k < seg_len;
+        env.item = act ? (int)__ldg(p.seg_idx + seg_s0 + seg_k) : 0;
+        env.item_raw = act ? 0 : n_items;  // FACTIVE reads item_raw < n_items
+        seg_k++;
+      } else {
         env.item_raw = gitem;
         env.item = gitem < last ? gitem : last;
-        continue;
       }
-      const bool act = seg_k < seg_len;
-      env.item = act ? (int)__ldg(p.seg_idx + seg_s0 + seg_k) : 0;
-      env.item_raw = act ? 0 : n_items;  // FACTIVE reads item_raw < n_items
-      seg_k++;
-      lo = p.body_start;
-    } else if (phase == 1 && warp_mode) {
+    } else if (warp_mode) {
       int blk = 0;
       if ((threadIdx.x & 31) == 0) blk = atomicAdd(p.counter, 1);
       blk = __shfl_sync(0xffffffffu, blk, 0);
-      if (blk >= p.n_blocks) {
-        phase = 2;
-        continue;
-      }
-      lo = p.body_start;
-      env.item_raw = blk * VM2_ITEMS_PER_WARP + (int)((threadIdx.x & 31) >> 1);
-    } else if (phase == 1) {
+      more = blk < p.n_blocks;
+      if (more) env.item_raw = blk * VM2_ITEMS_PER_WARP + (int)((threadIdx.x & 31) >> 1);
+    } else {
       __syncthreads();
       if (threadIdx.x == 0) s_blk = atomicAdd(p.counter, 1);
       __syncthreads();
       const int blk = s_blk;
-      if (blk >= p.n_blocks) {
-        phase = 2;
-        continue;
-      }
-      lo = p.body_start;
-      env.item_raw = blk * ITEMS + (int)(threadIdx.x >> 1);
-    } else {
-      lo = p.epi_start;
-      phase = 3;
+      more = blk < p.n_blocks;
+      if (more) env.item_raw = blk * ITEMS + (int)(threadIdx.x >> 1);
     }
-    vm2_run_section(env, p.code + lo);
+    pc = p.code + (more ? p.body_start : p.epi_start);
   }
   if (USE_TMEM) {
     tm_wait_st();

@@ -96,9 +96,9 @@ struct PairHostEnv {
     ld_own(slot, own);
     ld_oth(slot, oth);
     if (swap)
-      fp_mul2_inline(r, a, oth, b, own);
+      fp_mul2_looped(r, a, oth, b, own);
     else
-      fp_mul2_inline(r, a, own, b, oth);
+      fp_mul2_looped(r, a, own, b, oth);
   }
   void ld_lane_own(int slot, int off, fp& x) {
     if (slot >= sh->smem_slots) abort();      // TMEM lanes cannot be read by another thread
