@@ -96,7 +96,9 @@ struct Context {
   std::map<std::string, DevProgram> programs;
   uint64_t launches = 0;
   int ctas_per_sm = 0;   // launch shape: CTAs of 128 threads per SM (programs/registry.py); 0 = auto
-  int kernel = 2;        // 2 = paired kernel (two threads per item, vm_kernel2.cuh); 1 = one thread per item
+  // 1 = one thread per item (vm_kernel.cuh: the throughput kernel); 2 = two threads per item (vm_kernel2.cuh);
+  // environment variable B200BLS_KERNEL
+  int kernel = 1;
 };
 
 Context g_ctx;
@@ -144,7 +146,8 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   int grid = (int)(blocks_needed < max_grid ? blocks_needed : max_grid);
   if (grid < 1) grid = 1;
   if (grid_override > 0) grid = grid_override;
-  long long total = (long long)grid * nt;
+  // (sized for the largest grid of the shape: the warp-fetch policy below may spread a small batch over more CTAs)
+  long long total = (long long)(grid > max_grid ? grid : max_grid) * nt;
   StreamCtx& sc = cur();
   size_t cold_need = (size_t)pr.n_cold * 6 * sizeof(uint4) * total;
   if (cold_need > sc.cold_bytes) {
@@ -174,6 +177,25 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   if (seg) {
     p.seg_start = seg->start;
     p.seg_idx = seg->idx;
+  }
+  if (!pr.cross_thread && !seg) {
+    // item blocks of 32 per warp.  An isolated batch (automatic shape) is spread over all SMs and, when it is
+    // w.f waves long, runs as ceil(w.f) equal waves on fewer warps per CTA (a warp is faster at lower
+    // occupancy): 65,536 pairings = 1.15 waves took 1 + 1 passes, now two passes at 7 of 12 warps
+    const int warps = nt / 32;
+    p.warp_fetch = 1;
+    p.n_blocks = (long long)((n_items + 31) / 32);
+    p.active_warps = warps;
+    if (c.ctas_per_sm == 0 && grid_override == 0) {
+      const long long cap = max_grid * warps;
+      const long long waves = (p.n_blocks + cap - 1) / cap;
+      const long long per_wave = (p.n_blocks + waves - 1) / waves;
+      const int g2 = (int)(per_wave < max_grid ? per_wave : max_grid);
+      long long act = (per_wave + g2 - 1) / g2;
+      if (act < 1) act = 1;
+      if (act < warps) p.active_warps = (int)act;
+      if ((long long)g2 * nt <= total) grid = g2;   // never beyond what the cold area was sized for
+    }
   }
   p.smem_cells = 2 * pr.n_slots;
   for (int i = 0; i < n_bufs && i < VM_MAX_BUFS; i++) p.bufs[i] = bufs[i];
@@ -209,8 +231,9 @@ int launch_program2(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int
   if (grid < 1) grid = 1;
   if (seg) grid_override = (int)cta_blocks;  // one pair per segment, statically assigned
   if (grid_override > 0) grid = grid_override;
-  const long long total = (long long)grid * nt;  // threads
   StreamCtx& sc = cur();
+  // the cold area is sized for the largest grid of this shape: the warp-fetch policy below may raise `grid`
+  const long long total = (long long)(grid > max_grid ? grid : max_grid) * nt;  // threads
   const size_t cold_need = (size_t)pr.n_cold * 3 * sizeof(uint4) * total;
   if (cold_need > sc.cold_bytes) {
     CU(cudaStreamSynchronize(sc.stream));
@@ -242,15 +265,18 @@ int launch_program2(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int
   p.smem_cells = 2 * pr.n_slots;
   const int warps = nt / 32;
   if (!pr.cross_thread && !seg) {
-    // item blocks of 16 per warp.  An isolated batch (automatic shape) of w.f waves runs as ceil(w.f) EQUAL
-    // waves on fewer warps per CTA: each warp is faster at lower occupancy, the tail wave disappears.
+    // item blocks of 16 per warp.  An isolated batch (automatic shape) is spread over ALL SMs and, when it is
+    // w.f waves long, runs as ceil(w.f) EQUAL waves on fewer warps per CTA: a warp is faster at lower
+    // occupancy, so neither a partly filled last wave nor a handful of full CTAs on a few SMs is left.
     p.warp_fetch = 1;
     p.n_blocks = (long long)((n_items + VM2_ITEMS_PER_WARP - 1) / VM2_ITEMS_PER_WARP);
     p.active_warps = warps;
     if (c.ctas_per_sm == 0 && grid_override == 0) {
       const long long cap = max_grid * warps;
       const long long waves = (p.n_blocks + cap - 1) / cap;
-      long long act = (p.n_blocks + waves * grid - 1) / (waves * grid);
+      const long long per_wave = (p.n_blocks + waves - 1) / waves;      // warps busy at a time
+      grid = (int)(per_wave < max_grid ? per_wave : max_grid);
+      long long act = (per_wave + grid - 1) / grid;
       if (act < 1) act = 1;
       if (act < warps) p.active_warps = (int)act;
     }

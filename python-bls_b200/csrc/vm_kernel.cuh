@@ -345,7 +345,11 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) vm_kernel(const __grid_constant_
     __syncthreads();
     seg_iters = s_max;
   }
-  for (int phase = 0; phase < 3;) {
+  // programs without cross-thread reads: item blocks of 32 per WARP, by at most active_warps warps per CTA
+  // (no block-wide barrier in the item loop; see launch_program for the balanced-waves policy)
+  const bool warp_mode = p.warp_fetch != 0 && !seg_mode;
+  const bool warp_idle = warp_mode && (int)(threadIdx.x >> 5) >= p.active_warps;
+  for (int phase = warp_idle ? 3 : 0; phase < 3;) {
     int lo, hi;
     if (phase == 0) {
       lo = 0;
@@ -365,6 +369,18 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) vm_kernel(const __grid_constant_
       seg_k++;
       lo = p.body_start;
       hi = p.epi_start;
+    } else if (phase == 1 && warp_mode) {
+      int blk = 0;
+      if ((threadIdx.x & 31) == 0) blk = atomicAdd(p.counter, 1);
+      blk = __shfl_sync(0xffffffffu, blk, 0);
+      if (blk >= p.n_blocks) {
+        phase = 2;
+        continue;
+      }
+      lo = p.body_start;
+      hi = p.epi_start;
+      env.item_raw = (long long)blk * 32 + (threadIdx.x & 31);
+      env.item = env.item_raw < last ? env.item_raw : last;
     } else if (phase == 1) {
       // (tried: item blocks of 128 fetched per group of four warps through named barriers -- worse:
       // a wide CTA then stays resident until its slowest group is done and the next launch's CTA

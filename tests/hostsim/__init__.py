@@ -25,9 +25,18 @@ def lib():
     return _LIB
 
 
-def run(asm, bufs, strides, n_items, n_blocks=1, nt=4, honor_skips=True, paired=True):
+def run(asm, bufs, strides, n_items, n_blocks=1, nt=4, honor_skips=True, paired=None):
     """bufs: {id: np.uint8 array (modified in place)}; strides: {id: bytes per item, or item
-    capacity for raw SoA buffers}; nt = items per block; paired selects the executor (see lib())"""
+    capacity for raw SoA buffers}; nt = items per block; paired selects the executor (see lib()).
+    paired=None (default) runs BOTH executors -- the library ships both kernels -- and requires byte-identical
+    buffers from them."""
+    if paired is None:
+        twin = {i: b.copy() for i, b in bufs.items()}
+        run(asm, twin, strides, n_items, n_blocks, nt, honor_skips, paired=True)
+        run(asm, bufs, strides, n_items, n_blocks, nt, honor_skips, paired=False)
+        for i in bufs:
+            assert np.array_equal(bufs[i], twin[i]), "paired and one-thread executors disagree on buffer %d" % i
+        return bufs
     code = np.ascontiguousarray(asm.code).view(np.uint32).reshape(-1)
     consts = np.ascontiguousarray(asm.const_limbs())
     ptrs = (ctypes.c_void_p * 8)()

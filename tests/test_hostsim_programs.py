@@ -134,12 +134,15 @@ def test_sum_programs_with_skipped_and_executed_regions(g2):
         a1 = curve.build_sum_pass1(g2)().assemble(ns, n_tmem=ntm)
         a2 = curve.build_sum_pass2(g2)().assemble(ns, n_tmem=ntm)
         nb = 2
-        raw = np.zeros((3 if g2 else 2) * 6 * nb * 16, dtype=np.uint8)
-        hostsim.run(a1, {0: np.frombuffer(data, dtype=np.uint8).copy(), 1: raw}, {0: w, 1: nb}, n,
-                    n_blocks=nb, nt=128, honor_skips=honor)
-        out = np.zeros(w, dtype=np.uint8)
-        hostsim.run(a2, {0: raw, 1: out}, {0: nb, 1: w}, nb, n_blocks=1, nt=128, honor_skips=honor)
-        assert out.tobytes() == want
+        # raw (Montgomery-form, weakly reduced) intermediates are equal mod q, not byte for byte, between the two
+        # executors: each one is run end to end
+        for paired in (False, True):
+            raw = np.zeros((3 if g2 else 2) * 6 * nb * 16, dtype=np.uint8)
+            hostsim.run(a1, {0: np.frombuffer(data, dtype=np.uint8).copy(), 1: raw}, {0: w, 1: nb}, n,
+                        n_blocks=nb, nt=128, honor_skips=honor, paired=paired)
+            out = np.zeros(w, dtype=np.uint8)
+            hostsim.run(a2, {0: raw, 1: out}, {0: nb, 1: w}, nb, n_blocks=1, nt=128, honor_skips=honor, paired=paired)
+            assert out.tobytes() == want, paired
 
 
 def test_field_programs_on_weakly_reduced_edge_values():
@@ -186,13 +189,14 @@ def test_host_simulation_detects_cross_thread_hazards():
         asm.code = np.array(rows, dtype=np.uint16)
         pts = np.zeros(192 * 4, dtype=np.uint8)
         raw = np.zeros(3 * 6 * 1 * 16, dtype=np.uint8)
-        hostsim.run(asm, {0: pts, 1: raw}, {0: 192, 1: 1}, 4, n_blocks=1, nt=128)
+        hostsim.run(asm, {0: pts, 1: raw}, {0: 192, 1: 1}, 4, n_blocks=1, nt=128, paired=(sys.argv[2] == "paired"))
         print("finished")
     ''') % ([os.path.join(ROOT, d) for d in ('python-bls_b200', 'tests', 'oracle')],)
-    ok = subprocess.run([sys.executable, "-c", code, "clean"], capture_output=True, text=True)
-    assert ok.returncode == 0 and "finished" in ok.stdout, ok.stderr[-500:]
-    bad = subprocess.run([sys.executable, "-c", code, "inject"], capture_output=True, text=True)
-    assert bad.returncode != 0 and "finished" not in bad.stdout
+    for mode in ("single", "paired"):
+        ok = subprocess.run([sys.executable, "-c", code, "clean", mode], capture_output=True, text=True)
+        assert ok.returncode == 0 and "finished" in ok.stdout, ok.stderr[-500:]
+        bad = subprocess.run([sys.executable, "-c", code, "inject", mode], capture_output=True, text=True)
+        assert bad.returncode != 0 and "finished" not in bad.stdout
 
 
 @pytest.mark.parametrize("g2", [False, True])
