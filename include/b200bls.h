@@ -234,6 +234,29 @@ int b200bls_aggregate_verify_async(const uint8_t* sig, const uint8_t* pks, const
  * b200bls_final_exp_batch once. */
 int b200bls_aggregate_miller(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* out576);
 
+/* ---- multi-GPU: one process per GPU, contiguous batch slices -----------------------------------
+ * Independent units (pairing_batch, verify_batch) need no exchange.  The reductions exchange ONE tiny partial per
+ * rank -- a 576-byte Miller product (stage one of fq_ate_pairing_multi, fields_t.py:1114-1121) or one affine point
+ * -- with a single all-gather, and every rank finishes locally.  b200bls_comm_init joins the ranks of one node:
+ * `key` names the rendezvous (e.g. the launcher's MASTER_PORT), nccl_lib_path the NCCL library to dlopen (NULL:
+ * the system's libnccl.so.2; NCCL missing or failing leaves the shared-memory host gather, b200bls_comm_has_nccl
+ * tells).  use_nccl selects the transport per call: ncclAllGather over NVLink on the library stream, or a host
+ * gather through a POSIX shared-memory segment (north_star: measure both, keep the faster). */
+int b200bls_comm_init(int rank, int world, const char* key, const char* nccl_lib_path);
+void b200bls_comm_shutdown(void);
+int b200bls_comm_has_nccl(void);
+int b200bls_comm_world(void);
+int b200bls_comm_rank(void);
+/* The host gather on its own: `bytes` (<= 4096) per rank -> recv[world][bytes], in rank order, on every rank. */
+int b200bls_allgather_host(const uint8_t* send, uint8_t* recv, size_t bytes);
+/* bls.py:194-201 with the (pk_i, message hash_i) list sharded over the ranks: pks / mhs are this rank's slice
+ * (n may be 0), sig is read on rank 0.  The same *ok on every rank. */
+int b200bls_aggregate_verify_sharded(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, int use_nccl,
+                                     uint8_t* ok);
+/* bls.py:13-26 / 204-223 (plain sums) over device-resident slices: pts_dev = this rank's n affine points
+ * (96 / 192 bytes each); out = the sum over all ranks' slices as 96 / 192 host bytes, on every rank. */
+int b200bls_point_sum_sharded_dev(int g2, const void* pts_dev, size_t n, int use_nccl, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

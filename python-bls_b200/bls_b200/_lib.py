@@ -92,6 +92,14 @@ def _load():
         "b200bls_verify_batch": (i32, [vp, vp, vp, vp, sz]),
         "b200bls_verify_batch_dev": (i32, [vp, vp, vp, vp, sz]),
         "b200bls_aggregate_verify": (i32, [vp, vp, vp, sz, vp]),
+        "b200bls_comm_init": (i32, [i32, i32, c.c_char_p, c.c_char_p]),
+        "b200bls_comm_shutdown": (None, []),
+        "b200bls_comm_has_nccl": (i32, []),
+        "b200bls_comm_world": (i32, []),
+        "b200bls_comm_rank": (i32, []),
+        "b200bls_allgather_host": (i32, [vp, vp, sz]),
+        "b200bls_aggregate_verify_sharded": (i32, [vp, vp, vp, sz, i32, vp]),
+        "b200bls_point_sum_sharded_dev": (i32, [i32, vp, sz, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

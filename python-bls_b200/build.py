@@ -48,7 +48,7 @@ def build(force=False, verbose=True):
     srcs = [os.path.join(CSRC, f) for f in ("b200bls.cu", "microbench.cu")]
     deps = srcs + _walk(CSRC, (".cuh", ".h")) + [blob_o, os.path.join(ROOT, "include", "b200bls.h")]
     if force or _newer(LIB, deps):
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + [blob_o]
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + [blob_o, "-ldl", "-lrt"]
         if verbose:
             print(" ".join(cmd))
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/b200bls.h"
+#include "comm.cuh"
 #include "sha256.cuh"
 #include "vm_kernel.cuh"
 #include "vm_kernel2.cuh"
@@ -96,12 +97,15 @@ struct Context {
   std::map<std::string, DevProgram> programs;
   uint64_t launches = 0;
   int ctas_per_sm = 0;   // launch shape: CTAs of 128 threads per SM (programs/registry.py); 0 = auto
-  // 1 = one thread per item (vm_kernel.cuh: the throughput kernel); 2 = two threads per item (vm_kernel2.cuh);
-  // environment variable B200BLS_KERNEL
-  int kernel = 1;
+  // 1 = one thread per item (vm_kernel.cuh: the throughput kernel, 1.7 M pairings/s on whole waves); 2 = two
+  // threads per item (vm_kernel2.cuh: 0.7x the throughput, but 0.7x the latency of a pass -- 14.0 instead of
+  // 20.0 ms for up to 9,472 pairings); 0 = choose per launch: the paired kernel for isolated batches that leave
+  // most of the GPU empty, the one-thread kernel otherwise.  Environment variable B200BLS_KERNEL.
+  int kernel = 0;
 };
 
 Context g_ctx;
+Comm g_comm;
 std::mutex g_mu;
 // stream used by the calling THREAD's API calls (b200bls_set_stream): host threads that drive different
 // library streams do not disturb each other's selection
@@ -139,6 +143,10 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
                    const SegArgs* seg = nullptr) {
   Context& c = g_ctx;
   if (c.kernel == 2) return launch_program2(pr, n_items, bufs, n_bufs, grid_override, seg);
+  // automatic: latency-bound launches (at most one 128-item block per SM, no block reduction) go to the paired kernel
+  if (c.kernel == 0 && c.ctas_per_sm == 0 && grid_override == 0 && !seg && !pr.cross_thread &&
+      n_items <= (size_t)c.sm_count * 128)
+    return launch_program2(pr, n_items, bufs, n_bufs, grid_override, seg);
   const int nt = pr.threads;
   if (seg) grid_override = (int)((n_items + nt - 1) / nt);  // one thread per segment, statically assigned
   long long blocks_needed = (long long)((n_items + nt - 1) / nt);
@@ -178,15 +186,17 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
     p.seg_start = seg->start;
     p.seg_idx = seg->idx;
   }
-  if (!pr.cross_thread && !seg) {
-    // item blocks of 32 per warp.  An isolated batch (automatic shape) is spread over all SMs and, when it is
-    // w.f waves long, runs as ceil(w.f) equal waves on fewer warps per CTA (a warp is faster at lower
-    // occupancy): 65,536 pairings = 1.15 waves took 1 + 1 passes, now two passes at 7 of 12 warps
+  if (!pr.cross_thread && !seg && c.ctas_per_sm == 0 && grid_override == 0) {
+    // An isolated batch (automatic shape): item blocks of 32 per WARP, spread over all SMs, and when the batch
+    // is w.f waves long it runs as ceil(w.f) equal waves on fewer warps per CTA (a warp is faster at lower
+    // occupancy): 65,536 pairings = 1.15 waves took 33 + 32 ms, two passes at 7 of 12 warps take 52.  With an
+    // explicit shape (pipelines that keep launches in flight) blocks stay CTA-wide: the barrier per block keeps
+    // a CTA's warps near each other in the program, which the instruction cache rewards (33.1 vs 34.3 ms).
     const int warps = nt / 32;
     p.warp_fetch = 1;
     p.n_blocks = (long long)((n_items + 31) / 32);
     p.active_warps = warps;
-    if (c.ctas_per_sm == 0 && grid_override == 0) {
+    {
       const long long cap = max_grid * warps;
       const long long waves = (p.n_blocks + cap - 1) / cap;
       const long long per_wave = (p.n_blocks + waves - 1) / waves;
@@ -896,7 +906,7 @@ int b200bls_init(int device) {
     c.programs[nm] = dp;
   }
   const char* kenv = getenv("B200BLS_KERNEL");
-  if (kenv && (kenv[0] == '1' || kenv[0] == '2')) c.kernel = kenv[0] - '0';
+  if (kenv && kenv[0] >= '0' && kenv[0] <= '2') c.kernel = kenv[0] - '0';
   const char* env = getenv("B200BLS_CTAS_PER_SM");
   if (env && env[0] >= '0' && env[0] <= '4') c.ctas_per_sm = env[0] - '0';
   c.device = device;
@@ -1460,6 +1470,183 @@ int b200bls_aggregate_verify(const uint8_t* sig, const uint8_t* pks, const uint8
 int b200bls_aggregate_verify_async(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, uint8_t* ok) {
   std::lock_guard<std::mutex> lk(g_mu);
   return aggregate_verify_enqueue(sig, pks, mhs, n, ok);
+}
+
+// ---- multi-GPU: one process per GPU, one tiny all-gather per sharded reduction (comm.cuh) -------------------
+int b200bls_comm_init(int rank, int world, const char* key, const char* nccl_lib_path) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Comm& c = g_comm;   // (the host gather needs no GPU: the CPU-side tests of the multi-rank logic run it as is)
+  if (c.shm || c.world > 1) return fail(B200BLS_E_ARG, "communicator already initialised");
+  if (world < 1 || world > COMM_MAX_RANKS || rank < 0 || rank >= world) return fail(B200BLS_E_ARG, "bad rank %d / world %d", rank, world);
+  c.rank = rank;
+  c.world = world;
+  c.seq = 0;
+  if (world == 1) return 0;
+  snprintf(c.shm_name, sizeof(c.shm_name), "/b200bls_%s", key && key[0] ? key : "default");
+  int fd = -1;
+  if (rank == 0) {
+    shm_unlink(c.shm_name);   // a stale segment of a crashed run
+    fd = shm_open(c.shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, sizeof(CommShm)) != 0) return fail(B200BLS_E_ARG, "shm_open(%s) failed", c.shm_name);
+  } else {
+    for (int tries = 0; tries < 20000 && fd < 0; tries++) {   // wait for rank 0 (up to ~100 s)
+      fd = shm_open(c.shm_name, O_RDWR, 0600);
+      struct stat st;
+      if (fd >= 0 && (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(CommShm))) {
+        close(fd);
+        fd = -1;
+      }
+      if (fd < 0) usleep(5000);
+    }
+    if (fd < 0) return fail(B200BLS_E_ARG, "shared segment %s did not appear", c.shm_name);
+  }
+  void* m = mmap(nullptr, sizeof(CommShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return fail(B200BLS_E_ARG, "mmap of %s failed", c.shm_name);
+  c.shm = (CommShm*)m;   // a fresh segment is zero-filled: every flag starts at 0
+  c.shm->attached.fetch_add(1, std::memory_order_acq_rel);
+  if (!comm_wait(c.shm->attached, (uint32_t)world, 120.0)) return fail(B200BLS_E_ARG, "only %u of %d ranks attached", c.shm->attached.load(), world);
+  // NCCL (optional: the host gather works without it; needs an initialised GPU)
+  const char* names[3] = {nccl_lib_path, "libnccl.so.2", "libnccl.so"};
+  const bool want_nccl = g_ctx.ready && !getenv("B200BLS_NO_NCCL");   // (two ranks on ONE device: NCCL refuses)
+  for (int i = 0; i < 3 && !c.nccl_lib && want_nccl; i++)
+    if (names[i] && names[i][0]) c.nccl_lib = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+  if (c.nccl_lib) {
+    c.p_get_unique_id = (int (*)(NcclUniqueId*))dlsym(c.nccl_lib, "ncclGetUniqueId");
+    c.p_comm_init_rank = (int (*)(void**, int, NcclUniqueId, int))dlsym(c.nccl_lib, "ncclCommInitRank");
+    c.p_all_gather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(c.nccl_lib, "ncclAllGather");
+    c.p_comm_destroy = (int (*)(void*))dlsym(c.nccl_lib, "ncclCommDestroy");
+    c.p_error_string = (const char* (*)(int))dlsym(c.nccl_lib, "ncclGetErrorString");
+    const bool have = c.p_get_unique_id && c.p_comm_init_rank && c.p_all_gather && c.p_comm_destroy;
+    int rcn = have ? 0 : -1;
+    if (have && rank == 0) {
+      rcn = c.p_get_unique_id(&c.shm->nccl_id);
+      c.shm->id_ready.store(rcn == 0 ? 1u : 2u, std::memory_order_release);
+    }
+    if (have && rank != 0) {
+      if (!comm_wait(c.shm->id_ready, 1u, 120.0) || c.shm->id_ready.load() != 1u) rcn = -1;
+    }
+    if (rcn == 0) rcn = c.p_comm_init_rank(&c.nccl_comm, world, c.shm->nccl_id, rank);
+    if (rcn != 0) {
+      c.nccl_comm = nullptr;
+      fail(B200BLS_E_CUDA, "NCCL initialisation failed (%s); the host gather remains available",
+           c.p_error_string && rcn > 0 ? c.p_error_string(rcn) : "missing symbol or unique id");
+    } else {
+      CU(cudaMalloc(&c.gather_dev, (size_t)world * COMM_SLOT_BYTES));
+      CU(cudaMalloc(&c.send_dev, COMM_SLOT_BYTES));
+    }
+  }
+  return 0;
+}
+
+int b200bls_comm_has_nccl(void) { return g_comm.nccl_comm != nullptr; }
+
+// all-gather of `bytes` (<= 4096) host bytes per rank through the node's shared-memory segment
+int b200bls_allgather_host(const uint8_t* send, uint8_t* recv, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!send || !recv) return fail(B200BLS_E_ARG, "null buffer");
+  if (bytes > COMM_SLOT_BYTES) return fail(B200BLS_E_ARG, "payload of %zu bytes exceeds the exchange slot", bytes);
+  if (g_comm.world > 1 && !g_comm.shm) return fail(B200BLS_E_NOT_INIT, "communicator not initialised");
+  if (comm_allgather_host(g_comm, send, recv, bytes) != 0) return fail(B200BLS_E_CUDA, "host gather timed out");
+  return 0;
+}
+int b200bls_comm_world(void) { return g_comm.world; }
+int b200bls_comm_rank(void) { return g_comm.rank; }
+
+void b200bls_comm_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Comm& c = g_comm;
+  if (c.nccl_comm && c.p_comm_destroy) c.p_comm_destroy(c.nccl_comm);
+  if (c.gather_dev) cudaFree(c.gather_dev);
+  if (c.send_dev) cudaFree(c.send_dev);
+  if (c.shm) {
+    munmap(c.shm, sizeof(CommShm));
+    if (c.rank == 0) shm_unlink(c.shm_name);
+  }
+  c = Comm();
+}
+
+namespace {
+// all ranks' `bytes` (device, at src_dev) -> gathered_dev[world][bytes] on this rank, through NCCL or the host
+int gather_partials(const void* src_dev, size_t bytes, int use_nccl, void** gathered_dev) {
+  Comm& c = g_comm;
+  if (bytes > COMM_SLOT_BYTES) return fail(B200BLS_E_ARG, "partial of %zu bytes exceeds the exchange slot", bytes);
+  if (c.world == 1) {
+    *gathered_dev = (void*)src_dev;
+    return 0;
+  }
+  if (use_nccl) {
+    if (!c.nccl_comm) return fail(B200BLS_E_ARG, "NCCL gather requested but NCCL is not initialised");
+    int rc = c.p_all_gather(src_dev, c.gather_dev, bytes, /* ncclUint8 */ 1, c.nccl_comm, STREAM);
+    if (rc != 0) return fail(B200BLS_E_CUDA, "ncclAllGather failed: %s", c.p_error_string ? c.p_error_string(rc) : "?");
+    *gathered_dev = c.gather_dev;
+    return 0;
+  }
+  int rc = ensure_staging(5, (size_t)c.world * bytes);
+  if (rc) return rc;
+  static thread_local unsigned char mine[COMM_SLOT_BYTES];
+  static thread_local unsigned char all[COMM_MAX_RANKS * 1024];
+  if ((size_t)c.world * bytes > sizeof(all)) return fail(B200BLS_E_ARG, "host gather payload too large");
+  CU(cudaMemcpyAsync(mine, src_dev, bytes, cudaMemcpyDeviceToHost, STREAM));
+  CU(cudaStreamSynchronize(STREAM));
+  if (comm_allgather_host(c, mine, all, bytes) != 0) return fail(B200BLS_E_CUDA, "host gather timed out");
+  CU(cudaMemcpyAsync(cur().staging[5].ptr, all, (size_t)c.world * bytes, cudaMemcpyHostToDevice, STREAM));
+  *gathered_dev = cur().staging[5].ptr;
+  return 0;
+}
+}  // namespace
+
+// Aggregate verification with the (pk_i, message hash_i) pairs sharded over the ranks: pks / mhs are THIS
+// rank's slice (n may be 0), sig the aggregate signature (read on rank 0 only).  Every rank hashes and pairs
+// its slice in one fused launch, the 576-byte Miller products are all-gathered (use_nccl: ncclAllGather over
+// NVLink, else the shared-memory host gather), multiplied, and final-exponentiated once -- on every rank, so
+// every rank returns the same *ok (bls_py/bls.py:194-201 over a sharded message list).
+int b200bls_aggregate_verify_sharded(const uint8_t* sig, const uint8_t* pks, const uint8_t* mhs, size_t n, int use_nccl,
+                                     uint8_t* ok) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_READY();
+  if (!ok || (n && (!pks || !mhs))) return fail(B200BLS_E_ARG, "null buffer");
+  if (g_comm.rank == 0 && !sig) return fail(B200BLS_E_ARG, "rank 0 needs the signature");
+  int rc = aggregate_miller_host(g_comm.rank == 0 ? sig : nullptr, pks, mhs, n);
+  if (rc) return rc;
+  void* parts = nullptr;
+  if ((rc = gather_partials(cur().staging[3].ptr, 576, use_nccl, &parts))) return rc;
+  // product of the per-rank values: world - 1 Fq12 products on the device, then the final exponentiation check
+  if ((rc = ensure_staging(6, 576 + 16))) return rc;
+  uint8_t* acc = (uint8_t*)cur().staging[6].ptr;
+  CU(cudaMemcpyAsync(acc, parts, 576, cudaMemcpyDeviceToDevice, STREAM));
+  for (int r = 1; r < g_comm.world; r++) {
+    DevBuf db[3] = {{acc, 576}, {(uint8_t*)parts + 576 * (size_t)r, 576}, {acc, 576}};
+    if ((rc = run_dev("f12_mul", 1, db, 3))) return rc;
+  }
+  VmBuf b[2] = {vb(acc, 576), vb(acc + 576, 1)};
+  if ((rc = launch_named("final_exp_check", 1, b, 2))) return rc;
+  CU(cudaMemcpyAsync(ok, acc + 576, 1, cudaMemcpyDeviceToHost, STREAM));
+  CU(cudaStreamSynchronize(STREAM));
+  return 0;
+}
+
+// Sum of points sharded over the ranks (BLS.aggregate_sigs_simple / aggregate_pub_keys(secure=False),
+// bls.py:13-26, 204-223): pts_dev is THIS rank's device-resident slice of n affine points; every rank reduces
+// its slice to one affine point, the points are all-gathered and summed on every rank.  out: 96 / 192 host bytes.
+int b200bls_point_sum_sharded_dev(int g2, const void* pts_dev, size_t n, int use_nccl, uint8_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_READY();
+  if (!out) return fail(B200BLS_E_ARG, "null buffer");
+  const size_t w = g2 ? 192 : 96;
+  int rc = ensure_staging(6, 2 * w);
+  if (rc) return rc;
+  uint8_t* part = (uint8_t*)cur().staging[6].ptr;
+  if ((rc = sum_dev(g2 != 0, pts_dev, part, n))) return rc;
+  void* parts = nullptr;
+  if ((rc = gather_partials(part, w, use_nccl, &parts))) return rc;
+  if (g_comm.world > 1) {
+    if ((rc = sum_dev(g2 != 0, parts, part + w, (size_t)g_comm.world))) return rc;
+    part += w;
+  }
+  CU(cudaMemcpyAsync(out, part, w, cudaMemcpyDeviceToHost, STREAM));
+  CU(cudaStreamSynchronize(STREAM));
+  return 0;
 }
 
 }  // extern "C"
