@@ -1,21 +1,25 @@
 #!/usr/bin/env python3
-"""Benchmark of the b200-bls hot path (BASELINE.json config 2).
+"""Benchmark of the b200-bls hot path (BASELINE.json: pairings/s and signatures verified/s vs host CPU).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one batch of 65,536 independent full ate pairings (Miller loop + exact final
-exponentiation) per GPU on synthetic seeded inputs; weak scaling: every rank owns its own
-batch, no data-path collective.  Prints ONE JSON line on rank 0:
-  value        pairings/s with inputs resident in HBM, CUDA events on the library stream
-  e2e          the same through b200bls_pairing_batch() with pinned HOST buffers (H2D, kernel,
-               D2H inside the timed region)
-  roofline     integer-multiply roofline: algorithmic limb products / measured IMAD.WIDE peak
-  cpu_baseline the oracle port of the reference's CPU algorithm on all host cores
+One "step" = one batch of 65,536 independent full ate pairings (Miller loop + exact final exponentiation,
+BASELINE config 2) per GPU on synthetic seeded inputs; weak scaling: every rank owns its own batch, no data-path
+collective on this metric.  Rank 0 prints ONE JSON line:
+  value        pairings/s with inputs resident in HBM, CUDA events over the library streams
+  e2e          the same through the C-ABI host-buffer call (pinned HOST buffers: H2D, kernel, D2H in the timed region)
+  roofline     integer-multiply roofline: limb products the program executes / measured IMAD.WIDE peak
+  cpu_baseline the reference's own CPU implementation (unmodified, baseline/_ref) on all host cores, bounded sample;
+               its outputs double as the parity oracle for the sampled indices
+  extra        signatures verified/s, BASELINE configs 3 / 4 / 5 at full size with their parity booleans, the
+               isolated synchronous call, and -- under N > 1 -- the sharded reductions over BOTH exchange transports
 `--impl reference` times that CPU path alone with the same metric and config.
 """
 import argparse
+import hashlib
 import json
 import os
+import struct
 import subprocess
 import sys
 import threading
@@ -25,60 +29,169 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "python-bls_b200"))
 
 BATCH = 65536
-M_PER_PAIRING = 15200            # SURVEY.md 8d, frozen: efficient-algorithm Fq products per pairing
+M_NOMINAL = 15200                # SURVEY.md 8d, frozen: efficient-algorithm Fq products per pairing
+M_VERIFY_NOMINAL = 30400
 LIMB_PRODUCTS_PER_M = 300        # 12x12 limbs: 144 + 144 + 12
 METRIC = "pairings/s"
 WORKLOAD = "config2: 65,536 independent ate pairings (Miller loop + final exponentiation) per GPU"
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm, one process per host core
+# CPU arm: the reference itself (baseline/_ref, installed by tools/install_reference.py), else the oracle port
 # ---------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    seed, count = args
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import bls_oracle as O
-    p, q = O.aff_mul(seed * 2 + 3, O.G1), O.aff_mul(seed * 2 + 5, O.G2)
-    t = time.perf_counter()
-    for _ in range(count):
-        O.ate_pairing(p, q)
-    return time.perf_counter() - t
+def cpu_impl_kind():
+    return "reference" if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "bls_py")) else "port"
 
 
-def cpu_pairings_per_second(per_core=4, cores=None):
-    """oracle/bls_oracle.py ate_pairing on every host core -> (pairings/s, cores, sample text)"""
+def extmod_note():
+    try:
+        with open(os.path.join(ROOT, "baseline", "_ref", "STATUS.json")) as fh:
+            return json.load(fh)["extmod"]
+    except (OSError, ValueError, KeyError):
+        return "extmod: does not build in this image (no gmp.h; CPython-3.12-incompatible int access, SURVEY.md 8c)"
+
+
+_CPU = {}
+
+
+def _cpu_load(kind):
+    """per worker process: import the CPU implementation once"""
+    if kind in _CPU:
+        return _CPU[kind]
+    if kind == "reference":
+        import logging
+        logging.disable(logging.CRITICAL)          # the reference logs that its Cython accelerator is absent
+        sys.dont_write_bytecode = True
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        from bls_py import ec, pairing
+        from bls_py.fields import Fq, Fq2
+        q = ec.default_ec.q
+
+        def g1(raw):
+            return ec.AffinePoint(Fq(q, int.from_bytes(raw[:48], "big")), Fq(q, int.from_bytes(raw[48:], "big")),
+                                  False, ec.default_ec)
+
+        def g2(raw):
+            c = [int.from_bytes(raw[i:i + 48], "big") for i in range(0, 192, 48)]
+            return ec.AffinePoint(Fq2(q, c[0], c[1]), Fq2(q, c[2], c[3]), False, ec.default_ec_twist)
+
+        def mul1(k):
+            return (ec.generator_Fq().to_jacobian() * k).to_affine()
+
+        def mul2(k):
+            return (ec.generator_Fq2().to_jacobian() * k).to_affine()
+
+        def pair(p, qq):
+            return b"".join(c.to_bytes(48, "big") for c in pairing.ate_pairing(p, qq).ZT)
+
+        def verify(pk96, h, sig192):
+            from bls_py.aggregation_info import AggregationInfo
+            from bls_py.bls import BLS
+            from bls_py.keys import PublicKey
+            from bls_py.signature import Signature
+            pk = PublicKey.from_g1(g1(pk96).to_jacobian())
+            sig = Signature.from_g2(g2(sig192).to_jacobian(), AggregationInfo.from_msg_hash(pk, h))
+            return bool(BLS.verify(sig))
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import bls_oracle as O
+
+        def g1(raw):
+            return (int.from_bytes(raw[:48], "big"), int.from_bytes(raw[48:], "big"))
+
+        def g2(raw):
+            c = [int.from_bytes(raw[i:i + 48], "big") for i in range(0, 192, 48)]
+            return ((c[0], c[1]), (c[2], c[3]))
+
+        def mul1(k):
+            return O.aff_mul(k, O.G1)
+
+        def mul2(k):
+            return O.aff_mul(k, O.G2)
+
+        def pair(p, qq):
+            return O.f12_serialize(O.ate_pairing(p, qq))
+
+        def verify(pk96, h, sig192):
+            return bool(O.verify(g1(pk96) + (False,), h, g2(sig192) + (False,)))
+    _CPU[kind] = (g1, g2, mul1, mul2, pair, verify)
+    return _CPU[kind]
+
+
+def _cpu_pair_worker(task):
+    """task = (kind, [(idx, a, b, P bytes or None, Q bytes or None)]): inputs are built untimed (from the GPU's
+    own input bytes, or by the CPU implementation's scalar multiplication), only ate_pairing is timed"""
+    kind, items = task
+    g1, g2, mul1, mul2, pair, _ = _cpu_load(kind)
+    pts = [(idx, g1(bytes(P)) if P is not None else mul1(a), g2(bytes(Q)) if Q is not None else mul2(b))
+           for idx, a, b, P, Q in items]
+    t0 = time.perf_counter()
+    out = [(idx, pair(p, q)) for idx, p, q in pts]
+    return time.perf_counter() - t0, out
+
+
+def _cpu_verify_worker(task):
+    kind, items = task
+    verify = _cpu_load(kind)[5]
+    return [(idx, verify(bytes(pk), bytes(h), bytes(sig))) for idx, pk, h, sig in items]
+
+
+_POOL = {}
+
+
+def cpu_pool(cores):
     import multiprocessing as mp
+    if cores not in _POOL:
+        _POOL[cores] = mp.get_context("fork").Pool(cores)
+    return _POOL[cores]
+
+
+def cpu_pairings(items, cores=None, kind=None):
+    """ate_pairing of `items` = [(idx, a, b, P, Q)] on every host core -> (pairings/s, cores, {idx: 576 bytes}).
+    Throughput = items / max over workers of the time spent inside ate_pairing (one worker per core)."""
+    kind = kind or cpu_impl_kind()
     cores = cores or os.cpu_count() or 1
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(i, 1) for i in range(cores)])            # warm-up / import
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(i, per_core) for i in range(cores)])
-        dt = time.perf_counter() - t0
-    total = per_core * cores
-    return total / dt, cores, "%d pairings (%d per core on %d cores) of the same workload" % (total, per_core, cores)
+    pool = cpu_pool(cores)
+    chunks = [items[k::cores] for k in range(cores)]
+    res = pool.map(_cpu_pair_worker, [(kind, c) for c in chunks if c])
+    slowest = max(dt for dt, _ in res)
+    outs = {idx: raw for _, part in res for idx, raw in part}
+    return len(items) / slowest, cores, outs
+
+
+def sample_indices(seed, n, k):
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return sorted(int(i) for i in rng.choice(n, size=min(k, n), replace=False))
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU algorithm (oracle port: the reference is pure
-    Python and its Cython extension does not build in this image)"""
+    """--impl reference: the reference's own CPU implementation of the path (rank 0 only), a bounded sample of the
+    same workload per step: inputs P_i = a_i G1, Q_i = b_i G2 for seeded indices of config 2's scalars"""
     if rank != 0:
         return
-    times = []
+    from bls_b200 import synth
+    kind = cpu_impl_kind()
     cores = os.cpu_count() or 1
-    per_core = 3
+    a = synth.scalars(synth.SEED_PAIRING, BATCH)
+    b = synth.scalars(synth.SEED_PAIRING + 1, BATCH)
+    per_core = 2
+    idx_all = sample_indices(0xCB0, BATCH, per_core * cores * (args.warmup + args.steps))
+    vals = []
     for step in range(args.warmup + args.steps):
-        v, cores, sample = cpu_pairings_per_second(per_core=per_core)
+        idx = idx_all[step * per_core * cores:(step + 1) * per_core * cores]
+        items = [(i, int.from_bytes(bytes(a[i]), "big"), int.from_bytes(bytes(b[i]), "big"), None, None) for i in idx]
+        v, cores, _ = cpu_pairings(items, cores, kind)
         if step >= args.warmup:
-            times.append(v)
-        if step == 0 and args.warmup + args.steps > 4:
-            per_core = 2
-    value = sum(times) / len(times)
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    sample = "%d pairings per step (%d per core on %d cores) of the same seeded inputs" % (per_core * cores, per_core, cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / value,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (python int)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "python int (381-bit)",
             "data": "synthetic", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": kind, "sample": sample,
+                             "extmod": extmod_note()},
             "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -133,68 +246,63 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.samples), "power_w_max": max(pw) if pw else None}
 
 
+def build_id():
+    """identity of the kernel sources + embedded programs: an ncu capture only speaks for the build it was taken from"""
+    h = hashlib.sha256()
+    base = os.path.join(ROOT, "python-bls_b200", "csrc")
+    for nm in sorted(os.listdir(base)):
+        if nm.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(base, nm), "rb").read())
+    h.update(open(os.path.join(base, "gen", "programs.bin"), "rb").read())
+    return h.hexdigest()[:16]
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-def make_inputs(engine, synth, rank, n):
-    """P_i = a_i G1, Q_i = b_i G2 produced ON DEVICE by the scalar-multiplication kernels from
-    seeded scalars; returns device buffers (P, Q)"""
-    import numpy as np
-    from bls_b200.programs.curve import G1_GEN
-    from bls_b200.programs.hashg2 import G2_GEN
-    a = synth.scalars(synth.SEED_PAIRING + 2 * rank, n)
-    b = synth.scalars(synth.SEED_PAIRING + 2 * rank + 1, n)
-    g1 = np.frombuffer(b"".join(c.to_bytes(48, "big") for c in G1_GEN), dtype=np.uint8)
-    g2 = np.frombuffer(b"".join(c.to_bytes(48, "big") for c in (G2_GEN[0] + G2_GEN[1])), dtype=np.uint8)
-    dg1 = engine.DeviceBuffer(96 * n).upload(np.tile(g1, n))
-    dg2 = engine.DeviceBuffer(192 * n).upload(np.tile(g2, n))
-    da = engine.DeviceBuffer(32 * n).upload(a)
-    db = engine.DeviceBuffer(32 * n).upload(b)
-    dP, dQ = engine.DeviceBuffer(96 * n), engine.DeviceBuffer(192 * n)
-    from bls_b200._lib import check, lib
-    check(lib.b200bls_g1_scalar_mul_batch_dev(dg1.ptr, da.ptr, dP.ptr, n))
-    check(lib.b200bls_g2_scalar_mul_batch_dev(dg2.ptr, db.ptr, dQ.ptr, n))
-    check(lib.b200bls_sync())
-    for d in (dg1, dg2, da, db):
-        d.free()
-    return dP, dQ, a, b
-
-
-def run_gpu(args, rank, world, dist):
+def run_gpu(args, rank, world):
     import ctypes
     import numpy as np
-    from bls_b200 import _lib, engine, synth
+    from bls_b200 import _lib, distributed as D, engine, synth, workloads as W
     from bls_b200._lib import check, lib
+    from bls_b200.programs import registry
     local = int(os.environ.get("LOCAL_RANK", "0"))
     _lib.init(local)
-    # throughput shape: 4 = one 384-thread CTA per SM (6 shared + 7 Tensor-Memory slots per thread);
-    # batches overlap on two streams
-    check(lib.b200bls_set_ctas_per_sm(int(os.environ.get("B200BLS_BENCH_SHAPE", "4"))))
+    if world > 1:
+        D.init(rank, world)
+
+    def allmax(vals):
+        """max over ranks of a list of floats (host gather: timing plumbing only)"""
+        if world == 1:
+            return list(vals)
+        parts = D.gather_bytes(struct.pack("<%dd" % len(vals), *vals))
+        cols = [struct.unpack("<%dd" % len(vals), p) for p in parts]
+        return [max(c[k] for c in cols) for k in range(len(vals))]
+
+    def barrier():
+        check(lib.b200bls_sync())
+        if world > 1:
+            D.gather_bytes(b"\0")
+
+    # throughput shape (4 = 384 items per SM, CTA-wide item blocks) and two streams: consecutive batches overlap
+    SHAPE = int(os.environ.get("B200BLS_BENCH_SHAPE", "4"))
+    N_STREAMS = int(os.environ.get("B200BLS_BENCH_STREAMS", "2"))
+    check(lib.b200bls_set_ctas_per_sm(SHAPE))
     n = BATCH
-    # --- inputs: NSETS rotating buffer sets so the working set (NSETS * 56.6 MB) exceeds the
-    # 126 MB L2 between timed iterations
-    NSETS = 4
-    dP, dQ, a_sc, b_sc = make_inputs(engine, synth, rank, n)
+    NSETS = 4                      # rotating buffer sets: NSETS * 56.6 MB of inputs + outputs exceed the 126 MB L2
+    dP, dQ, a_sc, b_sc = W.config2_inputs(n, rank)
     sets = [(dP, dQ, engine.DeviceBuffer(576 * n))]
     hP, hQ = dP.download(), dQ.download()
     for _ in range(NSETS - 1):
-        p2, q2 = engine.DeviceBuffer(96 * n).upload(hP), engine.DeviceBuffer(192 * n).upload(hQ)
-        sets.append((p2, q2, engine.DeviceBuffer(576 * n)))
-
-    N_STREAMS = int(os.environ.get("B200BLS_BENCH_STREAMS", "2"))   # consecutive batches go to alternating library streams and overlap
+        sets.append((engine.DeviceBuffer(96 * n).upload(hP), engine.DeviceBuffer(192 * n).upload(hQ),
+                     engine.DeviceBuffer(576 * n)))
 
     def step(i):
         p, q, o = sets[i % NSETS]
         check(lib.b200bls_set_stream(i % N_STREAMS))
         check(lib.b200bls_pairing_batch_dev(p.ptr, q.ptr, o.ptr, n))
 
-    def barrier():
-        check(lib.b200bls_sync())
-        if dist is not None:
-            dist.barrier()
-
-    # --- integer-multiply peak, measured live (roofline denominator)
-    peak_ops, _ = engine.microbench_imad(3, 8, 256, 200)
+    peak_ops, _ = engine.microbench_imad(3, 8, 256, 200)     # integer-multiply peak, measured live
 
     for i in range(args.warmup):
         step(i)
@@ -211,14 +319,12 @@ def run_gpu(args, rank, world, dist):
     clocks = sampler.stop()
     check(lib.b200bls_set_stream(0))
 
-    # --- end to end through the host-buffer C ABI call, pinned host memory
+    # --- end to end through the host-buffer C ABI call, pinned host memory, one buffer set per stream
     def pinned(nbytes):
         p = lib.b200bls_host_alloc(nbytes)
         if not p:
             raise RuntimeError("pinned allocation failed")
         return p, np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes,))
-    # two pinned buffer sets, one per stream: consecutive batches overlap (copy of one with the
-    # kernel of the other, and the tail wave of one with the head of the next)
     host_sets = []
     for _ in range(N_STREAMS):
         pP, aP = pinned(96 * n)
@@ -242,124 +348,242 @@ def run_gpu(args, rank, world, dist):
     check(lib.b200bls_set_stream(0))
     aO = host_sets[(e2e_steps - 1) % N_STREAMS][3]
 
-    # --- parity spot check outside the timed region (rank 0): two outputs vs the oracle, and the
-    # device-resident result equals the host-path result
-    parity = None
-    if rank == 0:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import bls_oracle as O
-        dev_out = sets[(args.warmup + args.steps - 1) % NSETS][2].download()
-        parity = bool(np.array_equal(dev_out, aO))
-        for idx in (0, n - 1):
-            p = O.aff_mul(int.from_bytes(bytes(a_sc[idx]), "big"), O.G1)
-            q = O.aff_mul(int.from_bytes(bytes(b_sc[idx]), "big"), O.G2)
-            parity = parity and bytes(aO[576 * idx:576 * (idx + 1)]) == O.f12_serialize(O.ate_pairing(p, q))
+    # --- the isolated synchronous call a drop-in caller makes (automatic shape: balanced waves), host buffers
+    check(lib.b200bls_set_ctas_per_sm(0))
+    check(lib.b200bls_pairing_batch(host_sets[0][0], host_sets[0][1], host_sets[0][2], n))
+    lone = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter()
+        check(lib.b200bls_pairing_batch(host_sets[0][0], host_sets[0][1], host_sets[0][2], n))
+        lone = min(lone, time.perf_counter() - t0)
+    lone_same = bool(np.array_equal(host_sets[0][3], aO))
 
-    # --- secondary metric: signatures verified/s (hash-to-G2 + 2 Miller loops + final exp) on one
-    # full wave of VALID signatures sig_i = a_i H(m_i) for the public keys pk_i = a_i G1 = P_i
+    # --- parity (rank 0): sampled outputs vs the CPU implementation on the SAME input bytes (its timing is the
+    # cpu_baseline), device-resident result == host-path result, digest of the whole output buffer
+    parity, cpu = None, None
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        idx = sample_indices(0xB2C, n, 4 * cores)
+        items = [(i, 0, 0, hP[96 * i:96 * (i + 1)].tobytes(), hQ[192 * i:192 * (i + 1)].tobytes()) for i in idx]
+        cpu_v, cpu_cores, outs = cpu_pairings(items, cores)
+        dev_out = sets[(args.warmup + args.steps - 1) % NSETS][2].download()
+        match = all(aO[576 * i:576 * (i + 1)].tobytes() == outs[i] for i in idx)
+        parity = {"sampled_outputs_equal_cpu_%s" % cpu_impl_kind(): bool(match), "samples": len(idx),
+                  "device_path_equals_host_path": bool(np.array_equal(dev_out, aO)),
+                  "isolated_call_equals_streamed": lone_same,
+                  "output_sha256": hashlib.sha256(aO.tobytes()).hexdigest()}
+        cpu = {"value": cpu_v, "unit": METRIC, "cores": cpu_cores, "kind": cpu_impl_kind(),
+               "sample": "%d pairings (%d per core on %d cores) of this run's inputs at seeded indices; outputs compared "
+                         "with the GPU's" % (len(idx), len(idx) // cpu_cores, cpu_cores),
+               "extmod": extmod_note()}
+
+    # --- signatures verified/s (hash-to-G2 + 2 Miller loops + final exponentiation): one full wave of VALID
+    # signatures sig_i = a_i H(m_i) for the public keys pk_i = a_i G1 = P_i, throughput shape
+    check(lib.b200bls_set_ctas_per_sm(SHAPE))
     nv = lib.b200bls_sm_count() * 384
     mh = synth.message_hashes(synth.SEED_BATCH_VERIFY + rank, nv)
     d_mh = engine.DeviceBuffer(32 * nv).upload(mh)
     d_pk = engine.DeviceBuffer(96 * nv).upload(hP[:96 * nv])
-    d_sk = engine.DeviceBuffer(32 * nv).upload(a_sc[:nv])
     d_h = engine.DeviceBuffer(192 * nv)
-    d_sig = engine.DeviceBuffer(192 * nv)
-    d_ok = engine.DeviceBuffer(nv)
     check(lib.b200bls_hash_to_g2_batch_dev(d_mh.ptr, d_h.ptr, nv))
-    check(lib.b200bls_g2_scalar_mul_batch_dev(d_h.ptr, d_sk.ptr, d_sig.ptr, nv))
+    d_sig = W.dev_scalar_mul(a_sc[:nv], True, base=d_h)
+    d_ok = engine.DeviceBuffer(nv)
     check(lib.b200bls_verify_batch_dev(d_pk.ptr, d_mh.ptr, d_sig.ptr, d_ok.ptr, nv))
-    check(lib.b200bls_sync())
-    engine.timer_start()
-    for _ in range(3):
-        check(lib.b200bls_verify_batch_dev(d_pk.ptr, d_mh.ptr, d_sig.ptr, d_ok.ptr, nv))
-    verify_ms = engine.timer_stop() / 3
+    verify_ms = W.timed(lambda: check(lib.b200bls_verify_batch_dev(d_pk.ptr, d_mh.ptr, d_sig.ptr, d_ok.ptr, nv)))
     verify_all_ok = bool(d_ok.download().all())
-    # the same end to end from the wire formats: serialised keys (48 B) and signatures (96 B) in
-    # host memory -> H2D, from_bytes on the device, verification, D2H of the result bytes
     pk48 = engine.compress(d_pk.download(), False)
     sig96 = engine.compress(d_sig.download(), True)
     ok_wire = np.empty(nv, dtype=np.uint8)
     check(lib.b200bls_verify_batch_wire(_lib.ptr(pk48), _lib.ptr(mh), _lib.ptr(sig96), _lib.ptr(ok_wire), nv))
-    engine.timer_start()
-    check(lib.b200bls_verify_batch_wire(_lib.ptr(pk48), _lib.ptr(mh), _lib.ptr(sig96), _lib.ptr(ok_wire), nv))
-    verify_wire_ms = engine.timer_stop()
+    verify_wire_ms = W.timed(lambda: check(lib.b200bls_verify_batch_wire(_lib.ptr(pk48), _lib.ptr(mh), _lib.ptr(sig96),
+                                                                         _lib.ptr(ok_wire), nv)), reps=1)
     verify_all_ok = verify_all_ok and bool(ok_wire.all())
-    # pairings on a batch that is a whole number of waves (nv = one wave): the headline batch of
-    # 65,536 is 1.15 waves, so K of them end with a partly filled round (K = 5: 96 %)
     d_wo = engine.DeviceBuffer(576 * nv)
     check(lib.b200bls_pairing_batch_dev(d_pk.ptr, d_sig.ptr, d_wo.ptr, nv))
-    check(lib.b200bls_sync())
-    engine.timer_start()
-    for _ in range(3):
-        check(lib.b200bls_pairing_batch_dev(d_pk.ptr, d_sig.ptr, d_wo.ptr, nv))
-    wave_ms = engine.timer_stop() / 3
+    wave_ms = W.timed(lambda: check(lib.b200bls_pairing_batch_dev(d_pk.ptr, d_sig.ptr, d_wo.ptr, nv)))
+    for d in (d_mh, d_pk, d_h, d_sig, d_ok, d_wo):
+        d.free()
 
-    # --- reduce over ranks: max time
-    t = [ms, e2e_ms, verify_ms, verify_wire_ms, wave_ms]
-    if dist is not None:
-        import torch
-        tt = torch.tensor(t, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t = tt.tolist()
-    ms, e2e_ms, verify_ms, verify_wire_ms, wave_ms = t
+    # --- BASELINE configs 3, 4, 5 at full size (per GPU: the path shards by contiguous slices)
+    extra_cfg = run_configs(rank, world, allmax, barrier, D, W, engine, lib, check, np, synth, SHAPE)
+
+    t = allmax([ms, e2e_ms, verify_ms, verify_wire_ms, wave_ms, lone * 1e3])
+    ms, e2e_ms, verify_ms, verify_wire_ms, wave_ms, lone_ms = t
+    if world > 1:
+        D.shutdown()
     if rank != 0:
         return
     value = world * n * args.steps / (ms * 1e-3)
     e2e = world * n * e2e_steps / (e2e_ms * 1e-3)
     per_gpu = value / world
-    achieved = per_gpu * M_PER_PAIRING * LIMB_PRODUCTS_PER_M
+    executed_m = registry.executed_mults("pairing", 4)
+    executed_m_verify = registry.executed_mults("verify_full", 4)
+    achieved = per_gpu * executed_m * LIMB_PRODUCTS_PER_M
     hbm_bytes = n * (96 + 192 + 576)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    cpu_v, cpu_cores, cpu_sample = cpu_pairings_per_second(per_core=3)
-    # DRAM bytes of one launch of the pairing kernel at this batch size: dram__bytes_read.sum +
-    # dram__bytes_write.sum of the committed `ncu --set full` capture (tools/ncu_summary.py)
-    traffic = None
+    # DRAM bytes of one launch of the pairing kernel at this batch size from the committed `ncu --set full` capture,
+    # reported only if that capture was taken from THIS build (kernel sources + embedded programs)
+    traffic, traffic_note = None, "no ncu capture of this build under profiles/"
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_pairing_final_ncu.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2_pairing_ncu.json")) as fh:
             cap = json.load(fh)
-        if "n = 65,536" in cap["description"] and n == 65536 and lib.b200bls_get_ctas_per_sm() == 4:
+        if cap.get("build_id") == build_id():
             traffic = cap["dram_bytes_per_launch"]
+            traffic_note = "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r2_pairing_ncu.json (same build)"
+        else:
+            traffic_note = "profiles/r2_pairing_ncu.json is from build %s, this is %s: not reported" % (cap.get("build_id"), build_id())
     except (OSError, ValueError, KeyError):
         pass
-    from bls_b200.programs import registry
-    executed_m = registry.executed_mults("pairing", 4)
-    executed_m_verify = registry.executed_mults("verify_full", 4)
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Montgomery)",
         "data": "synthetic", "gpu_launches": int(launches),
         "config": {"workload": WORKLOAD, "batch_per_gpu": n, "l2": "inputs rotate over %d buffer sets (%d MB > L2)"
-                   % (NSETS, NSETS * hbm_bytes // 2 ** 20), "ctas_per_sm": lib.b200bls_get_ctas_per_sm(), "streams": N_STREAMS,
-                   "parity_spot_check": parity},
+                   % (NSETS, NSETS * hbm_bytes // 2 ** 20), "ctas_per_sm": SHAPE, "streams": N_STREAMS, "parity": parity},
         "e2e": {"value": e2e, "unit": METRIC, "h2d_bytes_per_step": n * 288, "d2h_bytes_per_step": n * 576,
                 "steps": e2e_steps, "api": "b200bls_pairing_batch_async + b200bls_sync (pinned host buffers, %d streams)" % N_STREAMS},
         "roofline": {"bound": "int32_mul", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
                      "unit": "T limb-products/s", "frac": achieved / peak_ops, "traffic": traffic,
                      "executed_M_per_unit": executed_m,
-                     "frac_executed": per_gpu * executed_m * LIMB_PRODUCTS_PER_M / peak_ops,
-                     "note": "achieved = pairings/s/GPU x 15,200 M x 300 limb products (SURVEY 8d, frozen efficient-"
-                             "algorithm count); frac_executed uses the Montgomery products the pairing program really "
-                             "executes (executed_M_per_unit, counted on the assembled code; inversions are ALU-pipe loops); peak = "
-                             "IMAD.WIDE.U32.X carry-chain microbenchmark measured in this run; per-launch "
-                             "algorithmic HBM bytes %d (%.4f of measured HBM peak at this rate); traffic = DRAM bytes of "
-                             "one launch from profiles/r1_pairing_final_ncu.json (workspace spills to the L2-backed cold area)"
-                             % (hbm_bytes, (per_gpu * 864 / 1e9) / peaks.get("hbm_gbs", 6553.3))},
-        "cpu_baseline": {"value": cpu_v, "unit": METRIC, "cores": cpu_cores, "kind": "port", "sample": cpu_sample},
+                     "frac_nominal": per_gpu * M_NOMINAL * LIMB_PRODUCTS_PER_M / peak_ops,
+                     "note": "frac = pairings/s/GPU x the Montgomery products the pairing program really executes "
+                             "(executed_M_per_unit, counted on the assembled code; inversions are ALU-pipe loops) x 300 limb "
+                             "products / the IMAD.WIDE.U32.X carry-chain peak measured in this run; frac_nominal uses SURVEY "
+                             "8d's frozen 15,200 M (work the program no longer does counts as done); algorithmic HBM bytes per "
+                             "launch %d (%.4f of the measured HBM peak at this rate); traffic: %s"
+                             % (hbm_bytes, (per_gpu * 864 / 1e9) / peaks.get("hbm_gbs", 6553.3), traffic_note)},
+        "cpu_baseline": cpu,
         "clocks": clocks,
-        "extra": {"verify_signatures_per_s": world * nv / (verify_ms * 1e-3), "verify_batch_per_gpu": nv, "verify_all_accepted": verify_all_ok,
-                  "verify_e2e_from_wire_bytes_per_s": world * nv / (verify_wire_ms * 1e-3),
-                  "pairings_per_s_whole_wave_batches": world * nv / (wave_ms * 1e-3),
-                  "whole_wave_roofline_frac": (nv / (wave_ms * 1e-3)) * M_PER_PAIRING * LIMB_PRODUCTS_PER_M / peak_ops,
-                  "verify_roofline_frac": (nv / (verify_ms * 1e-3)) * 30400 * 300 / peak_ops,
-                  "verify_executed_M_per_unit": executed_m_verify,
-                  "verify_roofline_frac_executed": (nv / (verify_ms * 1e-3)) * executed_m_verify * 300 / peak_ops},
+        "extra": dict({
+            "verify_signatures_per_s": world * nv / (verify_ms * 1e-3), "verify_batch_per_gpu": nv,
+            "verify_all_accepted": verify_all_ok,
+            "verify_e2e_from_wire_bytes_per_s": world * nv / (verify_wire_ms * 1e-3),
+            "verify_executed_M_per_unit": executed_m_verify,
+            "verify_roofline_frac": (nv / (verify_ms * 1e-3)) * executed_m_verify * 300 / peak_ops,
+            "verify_roofline_frac_nominal": (nv / (verify_ms * 1e-3)) * M_VERIFY_NOMINAL * 300 / peak_ops,
+            "pairings_per_s_whole_wave_batches": world * nv / (wave_ms * 1e-3),
+            "whole_wave_roofline_frac": (nv / (wave_ms * 1e-3)) * executed_m * 300 / peak_ops,
+            "isolated_synchronous_call": {"api": "b200bls_pairing_batch (pinned host buffers, automatic shape)",
+                                          "pairings": n, "ms": lone_ms, "pairings_per_s_per_gpu": n / (lone_ms * 1e-3)},
+            "build_id": build_id()}, **extra_cfg),
     }
     print(json.dumps(line), flush=True)
+
+
+def run_configs(rank, world, allmax, barrier, D, W, engine, lib, check, np, synth, shape):
+    """BASELINE configs 3, 4, 5 at full size.  Single-GPU numbers on every rank's own data (weak), and under N > 1
+    the SHARDED reductions (config 3 and 4 over all ranks' slices) through both exchange transports."""
+    out = {}
+    check(lib.b200bls_set_ctas_per_sm(0))
+    # ---- config 3: 1 M G2 signatures + 1 M G1 keys, plain sums (this GPU alone)
+    n3 = 1_000_000
+    c3 = {"n_points": n3}
+    for name, g2 in (("g2_signatures", True), ("g1_public_keys", False)):
+        w = 192 if g2 else 96
+        d_pts, cnt, tot = W.config3_slice(n3, g2)
+        d_sum = engine.DeviceBuffer(w)
+        fn = lib.b200bls_g2_sum_dev if g2 else lib.b200bls_g1_sum_dev
+        check(fn(d_pts.ptr, d_sum.ptr, cnt))
+        ms = W.timed(lambda: check(fn(d_pts.ptr, d_sum.ptr, cnt)))
+        ok = d_sum.download().tobytes() == W.expected_multiple(tot, g2)
+        ms = allmax([ms])[0]
+        c3[name] = {"ms": ms, "adds_per_s_per_gpu": (n3 - 1) / (ms * 1e-3), "parity_sum_equals_scalar_sum_times_G": bool(ok)}
+        d_pts.free()
+        d_sum.free()
+    out["config3_aggregate_1M"] = c3
+    # ---- config 4: aggregate verification of 10,000 distinct messages (10,001 Miller loops, one final exponentiation)
+    n4 = 10_000
+    agg, pks, hs, _ = W.config4_inputs(n4)
+    ok = engine.aggregate_verify(agg, pks, hs)
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ok = engine.aggregate_verify(agg, pks, hs) and ok
+        best = min(best, time.perf_counter() - t0)
+    hs_bad = hs.copy()
+    hs_bad[7] = hs[8]
+    rejected = not engine.aggregate_verify(agg, pks, hs_bad)
+    jobs = [(agg, pks, hs)] * 16
+    engine.aggregate_verify_many(jobs[:8])
+    dt = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter()
+        res = engine.aggregate_verify_many(jobs)
+        dt = min(dt, time.perf_counter() - t0)
+    best, dt = allmax([best, dt])
+    out["config4_aggregate_verify_10k"] = {
+        "n_messages": n4, "accepts": bool(ok), "rejects_swapped_message": bool(rejected),
+        "one_job_host_to_bool_ms": best * 1e3, "one_job_miller_loops_per_s": (n4 + 1) / best,
+        "jobs_in_flight": {"jobs": len(jobs), "all_accept": bool(all(res)), "seconds": dt,
+                           "miller_loops_per_s_per_gpu": len(jobs) * (n4 + 1) / dt}}
+    # ---- config 5: this GPU's share (500,000 = 4 M / 8) of independent verifications, 1 % corrupted
+    n5 = 500_000
+    check(lib.b200bls_set_ctas_per_sm(shape))
+    d_pk, d_hs, d_sig, want, (pk_h, hs_h, sig_h) = W.config5_inputs(n5, rank)
+    d_ok = engine.DeviceBuffer(n5)
+    check(lib.b200bls_verify_batch_dev(d_pk.ptr, d_hs.ptr, d_sig.ptr, d_ok.ptr, n5))
+    ms5 = W.timed(lambda: check(lib.b200bls_verify_batch_dev(d_pk.ptr, d_hs.ptr, d_sig.ptr, d_ok.ptr, n5)), reps=2)
+    res5 = d_ok.download()
+    all_match = bool(np.array_equal(res5, want))
+    cpu_ok = None
+    if rank == 0:            # CPU implementation's BLS.verify on 8 accepted + 8 corrupted triples
+        bad = np.flatnonzero(want == 0)[:8]
+        good = np.flatnonzero(want == 1)[:8]
+        items = [(int(i), pk_h[i].tobytes(), hs_h[i].tobytes(), sig_h[i].tobytes()) for i in list(good) + list(bad)]
+        cores = os.cpu_count() or 1
+        parts = cpu_pool(cores).map(_cpu_verify_worker, [(cpu_impl_kind(), items[k::cores]) for k in range(cores) if items[k::cores]])
+        cpu_ok = all(bool(res5[i]) == v for part in parts for i, v in part)
+    ms5 = allmax([ms5])[0]
+    out["config5_batch_verify"] = {"n_per_gpu": n5, "corrupted_per_gpu": int((want == 0).sum()), "ms": ms5,
+                                   "signatures_per_s": world * n5 / (ms5 * 1e-3),
+                                   "all_booleans_match_ground_truth": all_match,
+                                   "cpu_%s_verify_agrees_on_16_samples" % cpu_impl_kind(): cpu_ok}
+    for d in (d_pk, d_hs, d_sig, d_ok):
+        d.free()
+    check(lib.b200bls_set_ctas_per_sm(0))
+    # ---- N > 1: the sharded reductions, both transports (max over ranks; host buffers -> result on every rank)
+    if world > 1:
+        sh = {"nccl_initialised": bool(D.has_nccl()), "ranks": world}
+        transports = [("host_gather", False)] + ([("nccl_allgather", True)] if D.has_nccl() else [])
+        for n_tot in (1_000_000, 8_000_000):
+            d_pts, cnt, tot = W.config3_slice(n_tot, True, rank, world)
+            want_sum = W.expected_multiple(tot, True)
+            row = {}
+            for tname, nccl in transports:
+                got = D.point_sum(d_pts, True, use_nccl=nccl) if cnt else D.point_sum(b"", True, use_nccl=nccl)
+                barrier()
+                best = 1e30
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    got = D.point_sum(d_pts, True, use_nccl=nccl) if cnt else D.point_sum(b"", True, use_nccl=nccl)
+                    best = min(best, time.perf_counter() - t0)
+                    barrier()
+                row[tname] = {"ms": allmax([best * 1e3])[0], "parity": bool(got == want_sum)}
+            sh["config3_g2_sum_%dM_points" % (n_tot // 1_000_000)] = row
+            d_pts.free()
+        for n_tot in (10_000, 400_000):
+            agg, pks, hs, _ = W.config4_inputs(n_tot, seed=synth.SEED_AGG_VERIFY + (1 if n_tot > 10_000 else 0))
+            lo, hi = D.shard_range(n_tot, rank, world)
+            row = {}
+            for tname, nccl in transports:
+                ok = D.aggregate_verify(agg, pks[96 * lo:96 * hi], hs[lo:hi], use_nccl=nccl)
+                barrier()
+                best = 1e30
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    ok = D.aggregate_verify(agg, pks[96 * lo:96 * hi], hs[lo:hi], use_nccl=nccl) and ok
+                    best = min(best, time.perf_counter() - t0)
+                    barrier()
+                ms_ = allmax([best * 1e3])[0]
+                row[tname] = {"ms": ms_, "accepts": bool(ok), "miller_loops_per_s": (n_tot + 1) / (ms_ * 1e-3)}
+            sh["config4_aggregate_verify_%d_messages" % n_tot] = row
+        out["sharded_reductions"] = sh
+    return out
 
 
 def main():
@@ -376,16 +600,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29533")
-        dist_mod.init_process_group("gloo", rank=rank, world_size=world)
-        dist = dist_mod
-    run_gpu(args, rank, world, dist)
-    if dist is not None:
-        dist.destroy_process_group()
+    os.environ.setdefault("MASTER_PORT", "29533")
+    run_gpu(args, rank, world)
 
 
 if __name__ == "__main__":

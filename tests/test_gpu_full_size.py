@@ -1,0 +1,154 @@
+"""GPU parity at BASELINE.json's FULL sizes: seeded synthetic inputs built on the device, every
+result checked against its construction ground truth, and oracle samples of the sizes 8d asks for -- 256 seeded
+indices for config 2, 512 (>= 64 corrupted) for config 5 -- computed on all host cores."""
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import bls_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _g1(raw):
+    return (int.from_bytes(raw[:48], "big"), int.from_bytes(raw[48:], "big"))
+
+
+def _g2(raw):
+    c = [int.from_bytes(raw[i:i + 48], "big") for i in range(0, 192, 48)]
+    return ((c[0], c[1]), (c[2], c[3]))
+
+
+def _pair_worker(items):
+    return [(i, O.f12_serialize(O.ate_pairing(_g1(p), _g2(q)))) for i, p, q in items]
+
+
+def _verify_worker(items):
+    return [(i, bool(O.verify(_g1(pk) + (False,), h, _g2(sig) + (False,)))) for i, pk, h, sig in items]
+
+
+def _on_all_cores(fn, items):
+    cores = os.cpu_count() or 1
+    with mp.get_context("fork").Pool(cores) as pool:
+        parts = pool.map(fn, [items[k::cores] for k in range(cores) if items[k::cores]])
+    return dict(x for part in parts for x in part)
+
+
+def test_config2_65536_pairings_256_oracle_samples():
+    from bls_b200 import engine, workloads as W
+    from bls_b200._lib import check, lib
+    n = 65536
+    dP, dQ, a, b = W.config2_inputs(n)
+    hP, hQ = dP.download(), dQ.download()
+    # the inputs themselves: 64 random indices of the scalar-multiplication kernels vs the oracle
+    rng = np.random.Generator(np.random.PCG64(0xC2))
+    for i in rng.choice(n, size=64, replace=False):
+        assert hP[96 * i:96 * (i + 1)].tobytes() == b"".join(c.to_bytes(48, "big") for c in O.aff_mul(W.ints(a[i])[0], O.G1))
+    i = int(rng.integers(n))
+    q = O.aff_mul(W.ints(b[i])[0], O.G2)
+    assert hQ[192 * i:192 * (i + 1)].tobytes() == b"".join(c.to_bytes(48, "big") for c in (q[0][0], q[0][1], q[1][0], q[1][1]))
+    d_out = engine.DeviceBuffer(576 * n)
+    outs = {}
+    for shape in (0, 4):                      # the isolated-call policy (balanced waves) and the throughput shape
+        check(lib.b200bls_set_ctas_per_sm(shape))
+        check(lib.b200bls_pairing_batch_dev(dP.ptr, dQ.ptr, d_out.ptr, n))
+        outs[shape] = d_out.download()
+    check(lib.b200bls_set_ctas_per_sm(0))
+    assert np.array_equal(outs[0], outs[4])
+    out = outs[0]
+    idx = sorted(int(i) for i in rng.choice(n, size=256, replace=False))
+    want = _on_all_cores(_pair_worker, [(i, hP[96 * i:96 * (i + 1)].tobytes(), hQ[192 * i:192 * (i + 1)].tobytes()) for i in idx])
+    for i in idx:
+        assert out[576 * i:576 * (i + 1)].tobytes() == want[i], i
+    # size-independent property over ALL outputs: prod_i e(a_i G1, b_i G2) = e(G1, G2)^(sum a_i b_i)
+    prod = engine.field_op(12, "mul", out[:576 * (n // 2)], out[576 * (n // 2):])
+    while prod.size > 576:
+        h = prod.size // 1152 * 576
+        rest = prod[2 * h:]
+        prod = np.concatenate([engine.field_op(12, "mul", prod[:h], prod[h:2 * h]), rest])
+    e = sum(x * y for x, y in zip(W.ints(a), W.ints(b))) % O.N
+    base = engine.pairing_batch(hP[:0].tobytes() + b"".join(c.to_bytes(48, "big") for c in O.G1),
+                                b"".join(c.to_bytes(48, "big") for c in (O.G2[0] + O.G2[1])))
+    assert prod.tobytes() == engine.field_pow(12, base, [e]).tobytes()
+    for d in (dP, dQ, d_out):
+        d.free()
+
+
+@pytest.mark.parametrize("g2", [True, False])
+def test_config3_sum_of_one_million_points(g2):
+    from bls_b200 import engine, workloads as W
+    from bls_b200._lib import check, lib
+    n = 1_000_000
+    d_pts, cnt, tot = W.config3_slice(n, g2)
+    w = 192 if g2 else 96
+    d_sum = engine.DeviceBuffer(w)
+    check((lib.b200bls_g2_sum_dev if g2 else lib.b200bls_g1_sum_dev)(d_pts.ptr, d_sum.ptr, cnt))
+    p = O.aff_mul(tot, O.G2 if g2 else O.G1)               # the oracle's own scalar multiplication
+    want = b"".join(c.to_bytes(48, "big") for c in ((p[0][0], p[0][1], p[1][0], p[1][1]) if g2 else p))
+    assert d_sum.download().tobytes() == want
+    # the reference's left fold on a prefix (bls.py:13-26 / 204-223), and sub-range consistency
+    head = d_pts.download(w * 1000).reshape(1000, w)
+    fold = (O.g2_sum if g2 else O.g1_sum)([(_g2 if g2 else _g1)(r.tobytes()) for r in head])
+    fb = b"".join(c.to_bytes(48, "big") for c in ((fold[0][0], fold[0][1], fold[1][0], fold[1][1]) if g2 else fold))
+    assert engine.point_sum(head, g2).tobytes() == fb
+    d_pts.free()
+    d_sum.free()
+
+
+def test_config4_aggregate_verify_of_10000_messages():
+    from bls_b200 import engine, workloads as W
+    n = 10_000
+    agg, pks, hs, sks = W.config4_inputs(n)
+    assert engine.aggregate_verify(agg, pks, hs) is True
+    bad = hs.copy()
+    bad[4321] = hs[4322]
+    assert engine.aggregate_verify(agg, pks, bad) is False
+    wrong_key = pks.copy()
+    wrong_key[96 * 17:96 * 18] = pks[96 * 18:96 * 19]
+    assert engine.aggregate_verify(agg, wrong_key, hs) is False
+    # the final Fq12 value is one: e(-G1, sigma) * prod e(pk_i, H(m_i)) through the separate entry points
+    H = engine.hash_to_g2(hs)
+    neg_g1 = O.aff_neg(O.G1)
+    P = b"".join(c.to_bytes(48, "big") for c in neg_g1) + pks.tobytes()
+    assert engine.pairing_multi(P, agg.tobytes() + H.tobytes()).tobytes() == (1).to_bytes(48, "big") + bytes(528)
+    # product of Miller loops after the final exponentiation vs the oracle on a 64-pair subset
+    sub = list(range(0, 6400, 100))
+    Ps = [_g1(pks[96 * i:96 * (i + 1)].tobytes()) for i in sub]
+    Qs = [_g2(H[192 * i:192 * (i + 1)].tobytes()) for i in sub]
+    got = engine.pairing_multi(b"".join(pks[96 * i:96 * (i + 1)].tobytes() for i in sub),
+                               b"".join(H[192 * i:192 * (i + 1)].tobytes() for i in sub)).tobytes()
+    assert got == O.f12_serialize(O.ate_pairing_multi(Ps, Qs))
+    # several jobs in flight give the same answers
+    res = engine.aggregate_verify_many([(agg, pks, hs), (agg, pks, bad), (agg, pks, hs)])
+    assert res == [True, False, True]
+
+
+def test_config5_share_of_500000_verifications_512_oracle_samples():
+    from bls_b200 import engine, workloads as W
+    from bls_b200._lib import check, lib
+    n = 500_000
+    d_pk, d_hs, d_sig, want, (pk_h, hs_h, sig_h) = W.config5_inputs(n)
+    assert (want == 0).sum() == n // 100
+    d_ok = engine.DeviceBuffer(n)
+    check(lib.b200bls_verify_batch_dev(d_pk.ptr, d_hs.ptr, d_sig.ptr, d_ok.ptr, n))
+    res = d_ok.download()
+    assert np.array_equal(res, want)                         # all 500,000 booleans vs the construction ground truth
+    rng = np.random.Generator(np.random.PCG64(0xC5))
+    bad = rng.choice(np.flatnonzero(want == 0), size=96, replace=False)
+    good = rng.choice(np.flatnonzero(want == 1), size=416, replace=False)
+    items = [(int(i), pk_h[i].tobytes(), hs_h[i].tobytes(), sig_h[i].tobytes()) for i in list(good) + list(bad)]
+    oracle = _on_all_cores(_verify_worker, items)
+    assert len(oracle) == 512 and sum(1 for v in oracle.values() if not v) == 96
+    for i, v in oracle.items():
+        assert bool(res[i]) == v, i
+    # the same triples through the wire formats (decode on the device)
+    k = 4096
+    pk48 = engine.compress(pk_h[:k], False)
+    sig96 = engine.compress(sig_h[:k], True)
+    assert np.array_equal(engine.verify_batch_wire(pk48, hs_h[:k], sig96), want[:k])
+    for d in (d_pk, d_hs, d_sig, d_ok):
+        d.free()

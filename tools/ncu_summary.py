@@ -26,6 +26,20 @@ KEEP = [
 ]
 
 
+def build_id():
+    """same identity bench.py computes: kernel sources + embedded programs of the tree the capture was taken from (run
+    this script before changing them)"""
+    import hashlib
+    import os
+    base = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "python-bls_b200", "csrc")
+    h = hashlib.sha256()
+    for nm in sorted(os.listdir(base)):
+        if nm.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(base, nm), "rb").read())
+    h.update(open(os.path.join(base, "gen", "programs.bin"), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu(rep, page):
     return subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], stdout=subprocess.PIPE,
                           stderr=subprocess.DEVNULL, text=True, check=True).stdout
@@ -79,7 +93,8 @@ def main(rep, out, desc, index=0):
           "fmaheavy_pipe_pct": float(m["sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"][0]),
           "issue_active_pct": float(m["sm__issue_active.avg.pct_of_peak_sustained_elapsed"][0]),
           "registers_per_thread": int(m["launch__registers_per_thread"][0]),
-          "local_memory_instructions": int(float(m["sass__inst_executed_local_loads"][0])) + int(float(m["sass__inst_executed_local_stores"][0]))}
+          "local_memory_instructions": int(float(m["sass__inst_executed_local_loads"][0])) + int(float(m["sass__inst_executed_local_stores"][0])),
+          "build_id": build_id()}
     with open(out + "_ncu.json", "w") as fh:
         json.dump(js, fh, indent=1)
     print("\n".join(lines))
