@@ -97,11 +97,11 @@ def _cpu_load(kind):
         import bls_oracle as O
 
         def g1(raw):
-            return (int.from_bytes(raw[:48], "big"), int.from_bytes(raw[48:], "big"))
+            return (int.from_bytes(raw[:48], "big"), int.from_bytes(raw[48:], "big"), False)
 
         def g2(raw):
             c = [int.from_bytes(raw[i:i + 48], "big") for i in range(0, 192, 48)]
-            return ((c[0], c[1]), (c[2], c[3]))
+            return ((c[0], c[1]), (c[2], c[3]), False)
 
         def mul1(k):
             return O.aff_mul(k, O.G1)
@@ -113,7 +113,7 @@ def _cpu_load(kind):
             return O.f12_serialize(O.ate_pairing(p, qq))
 
         def verify(pk96, h, sig192):
-            return bool(O.verify(g1(pk96) + (False,), h, g2(sig192) + (False,)))
+            return bool(O.verify(g1(pk96), h, g2(sig192)))
     _CPU[kind] = (g1, g2, mul1, mul2, pair, verify)
     return _CPU[kind]
 
