@@ -410,9 +410,12 @@ def run_gpu(args, rank, world):
     t = allmax([ms, e2e_ms, verify_ms, verify_wire_ms, wave_ms, lone * 1e3])
     ms, e2e_ms, verify_ms, verify_wire_ms, wave_ms, lone_ms = t
     if world > 1:
+        barrier()
         D.shutdown()
     if rank != 0:
         return
+    if world > 1:
+        time.sleep(1.0)      # let the other ranks' exit chatter (NCCL_DEBUG lines share this stdout) precede the JSON line
     value = world * n * args.steps / (ms * 1e-3)
     e2e = world * n * e2e_steps / (e2e_ms * 1e-3)
     per_gpu = value / world

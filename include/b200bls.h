@@ -188,6 +188,14 @@ int b200bls_g2_decompress_batch(const uint8_t* in, uint8_t* out, uint8_t* ok, si
 int b200bls_g1_compress_batch(const uint8_t* in, uint8_t* out, size_t n);
 int b200bls_g2_compress_batch(const uint8_t* in, uint8_t* out, size_t n);
 
+/* The reference's Jacobian-coordinate functions on JACOBIAN inputs, the granularity of its plugin seam
+ * (fields_t.py:1218-1265): a = n x (X, Y, Z), three coordinates of 48 (G1) / 96 (G2) bytes, infinity = Z = 0.
+ * op 0: fq_/fq2_to_affine (fields_t.py:609-622); 1: fq_/fq2_double_point_jacobian (878-903); 2: fq_/fq2_
+ * add_points_jacobian with b = n Jacobian points (762-819; equal points double -- for G1 too, the reference's
+ * TypeError at 781 is a defect); 3: fq_/fq2_scalar_mult_jacobian with b = n x 32-byte big-endian scalars (705-740).
+ * out = n affine points (96 / 192 bytes, zero = infinity): the normalised representative (x, y, 1) of the triple
+ * the reference returns; the normalisation (two field inversions in the reference) runs on the device. */
+int b200bls_jacobian_op_batch(int g2, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 /* fq2_untwist (fields_t.py:936-943; ec.py:402-418 untwist): points of the twist E'(Fq2), 192 bytes, ->
  * (x / w^2, y / w^3) on E(Fq12): x' || y', 2 x 576 bytes. */
 int b200bls_g2_untwist_batch(const uint8_t* pts, uint8_t* out, size_t n);

@@ -49,6 +49,7 @@ def _load():
         "b200bls_field_pow_batch": (i32, [i32, vp, vp, vp, sz]),
         "b200bls_field_sqrt_batch": (i32, [i32, vp, vp, vp, sz]),
         "b200bls_sw_encode_g2_batch": (i32, [vp, vp, sz]),
+        "b200bls_jacobian_op_batch": (i32, [i32, i32, vp, vp, vp, sz]),
         "b200bls_g2_untwist_batch": (i32, [vp, vp, sz]),
         "b200bls_fq12_twist_batch": (i32, [vp, vp, sz]),
         "b200bls_g2_psi_batch": (i32, [vp, vp, sz]),

@@ -46,10 +46,10 @@ class Point:
         return tuple(c) if self.g2 else c[0]
 
     def to_affine(self):
-        return self
+        return self if type(self) is AffinePoint else _retype(self, AffinePoint)
 
     def to_jacobian(self):
-        return self
+        return self if type(self) is JacobianPoint else _retype(self, JacobianPoint)
 
     # -- arithmetic (one GPU call each; use bls_b200.engine for batches) ----------------------
     def __add__(self, other):
@@ -57,7 +57,7 @@ class Point:
             return self
         if not isinstance(other, Point) or other.g2 != self.g2:
             raise TypeError("cannot add %r" % type(other))
-        return Point(engine.point_add(self.raw, other.raw, self.g2).tobytes(), self.g2)
+        return JacobianPoint(engine.point_add(self.raw, other.raw, self.g2).tobytes(), self.g2)
 
     __radd__ = __add__
 
@@ -66,7 +66,7 @@ class Point:
             return self
         h = len(self.raw) // 2
         y = [(-int.from_bytes(self.raw[i:i + 48], "big")) % Q for i in range(h, 2 * h, 48)]
-        return Point(self.raw[:h] + b"".join(v.to_bytes(48, "big") for v in y), self.g2)
+        return type(self)(self.raw[:h] + b"".join(v.to_bytes(48, "big") for v in y), self.g2)
 
     def __neg__(self):
         return self.negate()
@@ -78,7 +78,7 @@ class Point:
         k = int(k)
         if k < 0 or k >> 256:
             k %= N                      # valid for points of order n (every public object here)
-        return Point(engine.scalar_mul(self.raw, k.to_bytes(32, "big"), self.g2).tobytes(), self.g2)
+        return JacobianPoint(engine.scalar_mul(self.raw, k.to_bytes(32, "big"), self.g2).tobytes(), self.g2)
 
     __rmul__ = __mul__
 
@@ -101,16 +101,96 @@ class Point:
         return "%s(%s)" % ("G2" if self.g2 else "G1", self.serialize().hex())
 
 
-# the reference exposes both coordinate systems; here they are one class
-AffinePoint = JacobianPoint = Point
+class AffinePoint(Point):
+    """ec.py:18-112.  Same storage as every Point here -- the canonical affine bytes; the class only records which
+    of the reference's two coordinate systems the caller asked for (to_affine / to_jacobian convert the class,
+    arithmetic returns Jacobian points like the reference's operators)."""
+    __slots__ = ()
 
 
-def generator_Fq():
-    return Point(b"".join(c.to_bytes(48, "big") for c in G1_GEN), False)
+class JacobianPoint(Point):
+    """ec.py:115-188: the reference's Jacobian triple, here always normalised (z = 1) and stored as affine bytes"""
+    __slots__ = ()
+
+    @property
+    def z(self):
+        if self.infinity:
+            return (0, 0) if self.g2 else 0
+        return (1, 0) if self.g2 else 1
 
 
-def generator_Fq2():
-    return Point(b"".join(c.to_bytes(48, "big") for c in (G2_GEN[0] + G2_GEN[1])), True)
+def _retype(p, cls):
+    q = cls(p.raw, p.g2)
+    q._ser = p._ser
+    return q
+
+
+class Fq12Point:
+    """an affine point with Fq12 coordinates, as ec.untwist / ec.twist return it (ec.py:402-437)"""
+    __slots__ = ("x", "y", "infinity")
+
+    def __init__(self, x, y, infinity=False):
+        self.x, self.y, self.infinity = x, y, infinity
+
+    def __eq__(self, other):
+        return isinstance(other, Fq12Point) and (self.x, self.y, self.infinity) == (other.x, other.y, other.infinity)
+
+    def __hash__(self):
+        return hash((self.x, self.y, self.infinity))
+
+
+def untwist(point, ec=None):
+    """ec.py:402-418: a point of the twist E'(Fq2) -> (x / w^2, y / w^3) on E(Fq12)"""
+    from .fields import Fq12
+    if isinstance(point, Fq12Point):          # fq12_untwist: divide the Fq12 coordinates by w^2, w^3
+        w2, w3 = _w_powers()
+        return Fq12Point(point.x / w2, point.y / w3, False)
+    if not point.g2:
+        raise Exception("point should be Fq2 or Fq12 elements")
+    out = engine.g2_untwist(point.raw).tobytes()
+    return Fq12Point(Fq12(out[:576]), Fq12(out[576:]), False)
+
+
+def twist(point, ec=None):
+    """ec.py:421-437: (x, y) -> (x w^2, y w^3) over Fq12"""
+    from .fields import Fq12
+    if isinstance(point, Fq12Point):
+        raw = point.x.raw + point.y.raw
+    else:                                     # an Fq2 point: its coordinates embedded at coefficient 0
+        raw = point.raw[:96] + bytes(480) + point.raw[96:] + bytes(480)
+    out = engine.fq12_twist(raw).tobytes()
+    return Fq12Point(Fq12(out[:576]), Fq12(out[576:]), False)
+
+
+def _w_powers():
+    from .fields import Fq12
+    w = Fq12(Q, (0,) * 6 + (1,) + (0,) * 5)
+    w2 = w * w
+    return w2, w2 * w
+
+
+def psi(P, ec=None):
+    """ec.py:440-444: twist(Frobenius(untwist(P))) on the twist's own coordinates"""
+    return JacobianPoint(engine.g2_psi(P.raw).tobytes(), True).to_affine()
+
+
+def sw_encode(t, ec=None, FE=None):
+    """ec.py:449-507 for t in Fq2 (an Fq2 field object, a pair of ints or 96 bytes): the Shallue-van de Woestijne
+    map onto the twist; t = 0 gives infinity.  (The Fq variant onto E(Fq) belongs to the G1 hash, which nothing on
+    the signature path uses: SURVEY.md section 2 marks it out of scope.)"""
+    raw = t.raw if hasattr(t, "raw") else (bytes(t) if isinstance(t, (bytes, bytearray)) else
+                                            b"".join((int(c) % Q).to_bytes(48, "big") for c in t))
+    if len(raw) != 96:
+        raise ValueError("sw_encode takes an Fq2 element")
+    return AffinePoint(engine.sw_encode_g2(raw).tobytes(), True)
+
+
+def generator_Fq(ec=None):
+    return AffinePoint(b"".join(c.to_bytes(48, "big") for c in G1_GEN), False)
+
+
+def generator_Fq2(ec=None):
+    return AffinePoint(b"".join(c.to_bytes(48, "big") for c in (G2_GEN[0] + G2_GEN[1])), True)
 
 
 def infinity(g2):
@@ -187,7 +267,7 @@ def hash_to_point_prehashed_Fq2(h):
         h = h.encode("utf-8")
     if len(h) != 32:
         raise ValueError("the batched hash-to-G2 takes 32-byte message hashes")
-    return Point(engine.hash_to_g2(bytes(h)).tobytes(), True)
+    return AffinePoint(engine.hash_to_g2(bytes(h)).tobytes(), True)
 
 
 def hash_to_point_Fq2(m):

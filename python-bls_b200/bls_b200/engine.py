@@ -83,6 +83,25 @@ def _map(fn, data, w_in, w_out):
     return out
 
 
+JACOBIAN_OPS = {"affine": 0, "dbl": 1, "add": 2, "mul": 3}
+
+
+def jacobian_op(op, a, b, g2):
+    """the reference's Jacobian-coordinate functions on n JACOBIAN points a = (X, Y, Z) (3 x 48 / 96 bytes, Z = 0 for
+    infinity): to_affine, double, add (b = n Jacobian points), scalar mult (b = n x 32-byte scalars) -> n AFFINE points"""
+    _lib.init()
+    a = as_u8(a)
+    w = 96 if g2 else 48
+    n = a.size // (3 * w)
+    if a.size != n * 3 * w:
+        raise ValueError("Jacobian points are %d bytes" % (3 * w))
+    opc = JACOBIAN_OPS[op]
+    bb = as_u8(b, n * (32 if opc == 3 else 3 * w)) if opc >= 2 else None
+    out = np.empty(n * 2 * w, dtype=np.uint8)
+    check(lib.b200bls_jacobian_op_batch(int(bool(g2)), opc, ptr(a), ptr(bb) if bb is not None else None, ptr(out), n))
+    return out
+
+
 def sw_encode_g2(t):
     """n x 96-byte Fq2 values -> n affine points of the twist (ec.py:449-507; infinity = zero bytes)"""
     return _map(lib.b200bls_sw_encode_g2_batch, t, 96, 192)

@@ -343,6 +343,36 @@ def build_bucket_fold(g2):
     return build
 
 
+def build_jacobian_op(g2, op):
+    """The reference's Jacobian-coordinate functions on JACOBIAN inputs (fields_t.py:609-632 to_affine, 705-740
+    scalar_mult_jacobian, 762-819 add_points_jacobian, 878-933 double_point_jacobian): buffers 0 = a = (X, Y, Z),
+    three coordinates of 48 / 96 bytes each (infinity: Z = 0), 1 = b (a second Jacobian point for "add", a 32-byte
+    scalar for "mul", unused otherwise), 2 = out, the result as an AFFINE point (zero bytes = infinity) -- the
+    normalised representative (x, y, 1) of the Jacobian triple the reference returns."""
+    def build():
+        prog = Program("%s_j%s" % ("g2" if g2 else "g1", op))
+        prog.begin_body()
+        c = Curve(prog, g2)
+        w = c.coord_bytes
+        p1 = (c.load(0, 0), c.load(0, w), c.load(0, 2 * w))
+        if op == "affine":
+            r = c.to_affine(p1)
+        elif op == "dbl":
+            r = c.to_affine(c.add(p1, p1))            # the complete addition: P + P doubles, infinity stays
+        elif op == "add":
+            p2 = (c.load(1, 0), c.load(1, w), c.load(1, 2 * w))
+            r = c.to_affine(c.add(p1, p2))
+        elif op == "mul":
+            x, y = c.to_affine(p1)
+            inf = x.is_zero() & y.is_zero()
+            r = c.to_affine(c.scalar_mul(x, y, inf, 1))
+        else:
+            raise ValueError(op)
+        c.store_affine(2, 0, r)
+        return prog
+    return build
+
+
 def build_decompress(g2):
     """Signature.from_bytes (bls_py/signature.py:22-38) / PublicKey.from_bytes
     (bls_py/keys.py:29-40): compressed x with the 'big y' flag in the top bit ->

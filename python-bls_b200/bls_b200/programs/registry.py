@@ -47,7 +47,6 @@ for _level in (1, 2):
 PROGRAMS["g2_untwist"] = extras.build_untwist
 PROGRAMS["f12_twist"] = extras.build_twist12
 PROGRAMS["g2_psi"] = extras.build_psi
-SHAPE1_ONLY = {"f1_pow", "f2_pow", "f6_pow", "f12_pow"} | {n for n in PROGRAMS if "_frob" in n}
 for _g2 in (False, True):
     _p = "g2" if _g2 else "g1"
     PROGRAMS[_p + "_mul"] = curve.build_scalar_mul(_g2)
@@ -56,8 +55,13 @@ for _g2 in (False, True):
     PROGRAMS[_p + "_sum2"] = curve.build_sum_pass2(_g2)
     PROGRAMS[_p + "_bucket"] = curve.build_bucket_fold(_g2)
     PROGRAMS[_p + "_decompress"] = curve.build_decompress(_g2)
+    for _op in ("affine", "dbl", "add", "mul"):        # the plugin seam's Jacobian-coordinate functions
+        PROGRAMS[_p + "_j" + _op] = curve.build_jacobian_op(_g2, _op)
     PROGRAMS[_p + "_cflag"] = curve.build_compress_flag(_g2)
 
+
+# programs assembled for the one-CTA-per-SM shape only (seam / parity utilities, never launched in bulk)
+SHAPE1_ONLY = {"f1_pow", "f2_pow", "f6_pow", "f12_pow"} | {n for n in PROGRAMS if "_frob" in n or "_j" in n}
 
 _M_WEIGHT = {"MUL2": 3, "SQR2": 2, "MULFP2": 2, "MUL1": 1, "SQR1": 1, "LDBE48": 1, "LDBE32": 1, "STBE48": 1, "FGTHALF": 1,
              "INV1": 2}

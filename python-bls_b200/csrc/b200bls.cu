@@ -1126,6 +1126,18 @@ int b200bls_field_sqrt_batch(int level, const uint8_t* a, uint8_t* out, uint8_t*
   return run_host(level == 1 ? "f1_sqrt" : "f2_sqrt", n, hb, 3);
 }
 
+int b200bls_jacobian_op_batch(int g2, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  static const char* kOps[4] = {"affine", "dbl", "add", "mul"};
+  if (op < 0 || op > 3) return fail(B200BLS_E_ARG, "jacobian_op: op %d (0 to_affine, 1 double, 2 add, 3 scalar mult)", op);
+  if (!a || !out || (op >= 2 && !b)) return fail(B200BLS_E_ARG, "null buffer");
+  char name[32];
+  snprintf(name, sizeof(name), "%s_j%s", g2 ? "g2" : "g1", kOps[op]);
+  const size_t w = g2 ? 96 : 48;
+  HostBuf hb[3] = {{a, nullptr, 3 * w}, {op >= 2 ? b : nullptr, nullptr, op == 3 ? (size_t)32 : 3 * w}, {nullptr, out, 2 * w}};
+  return run_host(name, n, hb, 3);
+}
+
 int b200bls_sw_encode_g2_batch(const uint8_t* t, uint8_t* out, size_t n) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!t || !out) return fail(B200BLS_E_ARG, "null buffer");

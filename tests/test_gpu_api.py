@@ -100,3 +100,34 @@ def test_batch_verify_api():
     assert BLS.verify_batch(pks, hs, sigs) == [True] * 4
     sigs[2] = sigs[1]
     assert BLS.verify_batch(pks, hs, sigs) == [True, True, False, True]
+
+
+def test_ec_module_mirrors_untwist_twist_psi_sw_encode_and_point_classes():
+    """bls_b200.ec offers the reference's names (ec.py:18-188 AffinePoint / JacobianPoint, 402-444 untwist / twist /
+    psi, 449-507 sw_encode) with the reference's values"""
+    import bls_oracle as O
+    from bls_b200 import ec
+    from bls_b200.fields import Fq2, Fq12, Q
+    from conftest import load_golden
+    g2 = ec.generator_Fq2()
+    assert isinstance(g2, ec.AffinePoint) and isinstance(g2.to_jacobian(), ec.JacobianPoint)
+    p = g2.to_jacobian() * 5
+    assert isinstance(p, ec.JacobianPoint) and isinstance(p.to_affine(), ec.AffinePoint)
+    assert p == p.to_affine() and hash(p) == hash(p.to_affine()) and p.to_jacobian().z == (1, 0)
+    op = O.aff_mul(5, O.G2)
+    u = ec.untwist(p)
+    ux, uy, _ = O.untwist((op[0], op[1], False))
+    assert u.x.ZT == ux and u.y.ZT == uy
+    back = ec.twist(u)
+    assert back.x == Fq12.from_fq(Q, Fq2(Q, *op[0])) or back.x.ZT == tuple(op[0]) + (0,) * 10
+    assert back.y.ZT == tuple(op[1]) + (0,) * 10
+    assert ec.untwist(ec.twist(u)) == u                       # fq12_untwist . fq12_twist
+    for c in load_golden("hash_kat.json")["psi"]:
+        pt = ec.AffinePoint(bytes.fromhex(c["p"]["x"] + c["p"]["y"]), True)
+        assert ec.psi(pt).raw.hex() == c["out"]["x"] + c["out"]["y"]
+    for c in load_golden("hash_kat.json")["sw_encode"][:6]:
+        t = bytes.fromhex(c["t"])
+        got = ec.sw_encode(Fq2(t))
+        assert got.infinity == c["out"]["inf"]
+        if not got.infinity:
+            assert got.raw.hex() == c["out"]["x"] + c["out"]["y"]
