@@ -41,7 +41,7 @@ __device__ __forceinline__ uint32_t dfma_body(int iters, uint32_t seed) {
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(256) imad_kernel(uint32_t* out, int iters, uint32_t seed) {
+__global__ void __launch_bounds__(1024) imad_kernel(uint32_t* out, int iters, uint32_t seed) {
   if (VARIANT == 4 || (VARIANT == 5 && ((threadIdx.x >> 5) & 1))) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = dfma_body(iters, seed);
     return;
@@ -70,6 +70,16 @@ __global__ void __launch_bounds__(256) imad_kernel(uint32_t* out, int iters, uin
           lo[c] = (uint32_t)acc;
           hi[c] = (uint32_t)(acc >> 32);
         }
+      } else if (VARIANT == 6) {
+        // FOUR independent carry chains of two column pairs each, interleaved by the compiler: the instruction-level
+        // parallelism a Montgomery round really has (variant 3 is one serial chain)
+#pragma unroll
+        for (int c = 0; c < CHAINS; c += 2) {
+          asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(lo[c]) : "r"(a), "r"(b));
+          asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(hi[c]) : "r"(a), "r"(b));
+          asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(lo[c + 1]) : "r"(a), "r"(b));
+          asm volatile("madc.hi.u32 %0, %1, %2, %0;" : "+r"(hi[c + 1]) : "r"(a), "r"(b));
+        }
       } else {
         // one carry chain across the 8 column pairs, exactly like a row of fp_mul
         asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(lo[0]) : "r"(a), "r"(b));
@@ -97,7 +107,7 @@ extern "C" int b200bls_microbench_imad(int variant, int blocks_per_sm, int threa
   if (cudaGetDevice(&dev) != cudaSuccess) return B200BLS_E_CUDA;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return B200BLS_E_CUDA;
-  if (threads < 32 || threads > 256 || blocks_per_sm < 1) return B200BLS_E_ARG;
+  if (threads < 32 || threads > 1024 || blocks_per_sm < 1) return B200BLS_E_ARG;
   const int blocks = prop.multiProcessorCount * blocks_per_sm;
   uint32_t* out = nullptr;
   if (cudaMalloc(&out, (size_t)threads * blocks * 4) != cudaSuccess) return B200BLS_E_NOMEM;
@@ -113,6 +123,7 @@ extern "C" int b200bls_microbench_imad(int variant, int blocks_per_sm, int threa
       case 2: imad_kernel<2><<<blocks, threads>>>(out, iters, 12345u + rep); break;
       case 4: imad_kernel<4><<<blocks, threads>>>(out, iters, 12345u + rep); break;
       case 5: imad_kernel<5><<<blocks, threads>>>(out, iters, 12345u + rep); break;
+      case 6: imad_kernel<6><<<blocks, threads>>>(out, iters, 12345u + rep); break;
       default: imad_kernel<3><<<blocks, threads>>>(out, iters, 12345u + rep); break;
     }
     cudaEventRecord(e1);
