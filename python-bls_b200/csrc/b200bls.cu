@@ -19,8 +19,8 @@
 #include "../../include/b200bls.h"
 #include "comm.cuh"
 #include "sha256.cuh"
-#include "vm_kernel.cuh"
-#include "vm_kernel2.cuh"
+#include "gen/vm_isa.h"
+#include "vm_launch.h"
 
 using namespace b200bls;
 
@@ -215,14 +215,11 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
     if (pr.n_tmem * 24 > 168) return fail(B200BLS_E_PROGRAM, "wide shape: %d TMEM slots do not fit 168 columns", pr.n_tmem);
     p.tmem_cols = 512;
     p.tmem_group_cols = 168;
-    vm_kernel<true, 1, VM_NT_WIDE><<<grid, VM_NT_WIDE, smem, sc.stream>>>(p);
+    vm1_launch(true, true, grid, smem, sc.stream, p);
   } else {
     p.tmem_cols = pr.n_tmem == 0 ? 0 : (pr.n_tmem * 24 <= 128 ? 128 : (pr.n_tmem * 24 <= 256 ? 256 : 512));
     p.tmem_group_cols = 0;
-    if (p.tmem_cols)
-      vm_kernel<true, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
-    else
-      vm_kernel<false, 3><<<grid, VM_NT, smem, sc.stream>>>(p);
+    vm1_launch(p.tmem_cols != 0, false, grid, smem, sc.stream, p);
   }
   CU(cudaGetLastError());
   c.launches++;
@@ -301,22 +298,7 @@ int launch_program2(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int
   const int cols = groups * p.tmem_group_cols;
   p.tmem_cols = cols == 0 ? 0 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512));
   if (cols > 512) return fail(B200BLS_E_PROGRAM, "%d TMEM slots do not fit 512 columns", pr.n_tmem);
-  if (nt == VM2_NT_WIDE) {
-    if (seg)
-      vm2_kernel<true, VM2_NT_WIDE, 2, true><<<grid, nt, smem, sc.stream>>>(p);
-    else
-      vm2_kernel<true, VM2_NT_WIDE, 2><<<grid, nt, smem, sc.stream>>>(p);
-  } else if (p.tmem_cols) {
-    if (seg)
-      vm2_kernel<true, VM2_NT, 3, true><<<grid, nt, smem, sc.stream>>>(p);
-    else
-      vm2_kernel<true, VM2_NT, 3><<<grid, nt, smem, sc.stream>>>(p);
-  } else {
-    if (seg)
-      vm2_kernel<false, VM2_NT, 3, true><<<grid, nt, smem, sc.stream>>>(p);
-    else
-      vm2_kernel<false, VM2_NT, 3><<<grid, nt, smem, sc.stream>>>(p);
-  }
+  vm2_launch(p.tmem_cols != 0, nt == VM2_NT_WIDE, seg != nullptr, grid, smem, sc.stream, p);
   CU(cudaGetLastError());
   c.launches++;
   return 0;
@@ -849,15 +831,8 @@ int b200bls_init(int device) {
   }
   CU(cudaEventCreate(&c.ev0));
   CU(cudaEventCreate(&c.ev1));
-  CU(cudaFuncSetAttribute(vm_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  CU(cudaFuncSetAttribute(vm_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  CU(cudaFuncSetAttribute(vm_kernel<true, 1, VM_NT_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  CU(cudaFuncSetAttribute(vm2_kernel<false, VM2_NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  CU(cudaFuncSetAttribute(vm2_kernel<true, VM2_NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  CU(cudaFuncSetAttribute(vm2_kernel<true, VM2_NT_WIDE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-  CU(cudaFuncSetAttribute(vm2_kernel<false, VM2_NT, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  CU(cudaFuncSetAttribute(vm2_kernel<true, VM2_NT, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  CU(cudaFuncSetAttribute(vm2_kernel<true, VM2_NT_WIDE, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+  CU(vm1_configure());
+  CU(vm2_configure());
   // parse the embedded program blob
   const unsigned char* blob = _binary_programs_bin_start;
   size_t blob_len = (size_t)(_binary_programs_bin_end - _binary_programs_bin_start);

@@ -308,8 +308,8 @@ __device__ __forceinline__ uint32_t fp_funnel_r(uint32_t lo, uint32_t hi, int s)
 inline
 #else
 // out of line: a cold loop that must not perturb the interpreter's register allocation or sit
-// between its hot opcode bodies in the instruction cache
-__device__ __noinline__
+// between its hot opcode bodies in the instruction cache (internal linkage: one copy per kernel translation unit)
+static __device__ __noinline__
 #endif
 bool fp_is_square(fp x) {
   fp a, n;
@@ -593,7 +593,7 @@ FP_DEV void fp_mul(fp& r, const fp& a, const fp& b) { fp_mul_inline(r, a, b); }
 // (ptxas: 0 bytes stack).  Unrolled: measured against the looped form (531 instead of ~400 executed
 // instructions per call through the rotation of b and the zeroed accumulators; the 150 instructions it saves
 // do not decide whether the hot code fits the instruction cache).
-__device__ __noinline__ fp fp_mul_call(fp a, fp b) {
+static __device__ __noinline__ fp fp_mul_call(fp a, fp b) {
   fp r;
   fp_mul_inline(r, a, b);
   return r;
@@ -627,7 +627,7 @@ __device__ __forceinline__ constexpr uint32_t r2inv_limb(int i) {
   return t[i];
 }
 #define R2INVL(i) r2inv_limb(i)
-__device__ __noinline__
+static __device__ __noinline__
 #endif
 fp fp_inv(fp x) {
   fp a, n, ra, rn;

@@ -12,42 +12,9 @@
 #include <cuda_runtime.h>
 
 #include "vm_exec.cuh"
+#include "vm_params.h"
 
 namespace b200bls {
-
-constexpr int VM_NT = 128;      // threads per CTA (default shapes)
-constexpr int VM_NT_WIDE = 384; // "wide" shape: ONE CTA of 12 warps per SM.  Three 128-thread CTAs can only
-                                // allocate 128 TMEM columns each (power-of-two allocations, 512 per SM); one CTA
-                                // owns all 512 and gives each group of four warps 168 columns = 7 Fq2 slots
-constexpr int VM_MAX_BUFS = 8;
-
-struct VmBuf {
-  unsigned char* ptr;
-  long long stride;  // bytes per item (byte buffers) or item capacity (raw SoA buffers)
-};
-
-struct VmParams {
-  const uint2* code;       // instructions, padded with one trailing NOP
-  int body_start, epi_start, n_ins;
-  const uint4* consts;     // Montgomery-form constants, 3 x uint4 each
-  uint4* cold;             // [n_cold * 6][total threads]
-  long long n_items;
-  long long n_blocks;      // ceil(n_items / CTA threads): item blocks handed out dynamically
-  int* counter;            // zeroed before the launch; next item block to process
-  int smem_cells;          // cells [0, smem_cells) live in shared memory, the rest in Tensor Memory
-  int tmem_cols;           // TMEM columns to allocate per CTA (0, 128, 256 or 512)
-  int tmem_group_cols;     // columns owned by each group of four warps (CTAs wider than 128 threads)
-  // Segmented mode (multi-scalar multiplication buckets): thread t owns segment t of `n_items`
-  // segments; body iteration k processes record seg_idx[seg_start[t] + k] of the indexed buffers
-  // (inactive once k reaches the segment length); prologue / epilogue address record t.
-  const unsigned* seg_start;  // n_items + 1 offsets into seg_idx, or nullptr (normal mode)
-  const unsigned* seg_idx;
-  // paired kernel (vm_kernel2.cuh): item blocks of 16 handed out per warp (programs without
-  // cross-thread reads), by at most active_warps warps of every CTA
-  int warp_fetch;
-  int active_warps;
-  VmBuf bufs[VM_MAX_BUFS];
-};
 
 // ---- Tensor Memory as per-thread scratch --------------------------------------------------------
 // TMEM is 512 columns x 128 lanes x 32 bit per SM.  With the 32x32b access shape, thread i of
@@ -289,7 +256,11 @@ __device__ __forceinline__ void vm_run_section(Env& env, const uint2* code, int 
 // executes relinquish_alloc_permit or exits, which serialises co-resident CTAs -- see
 // tools/experiments/tmem_residency_test.cu.  Hence two instantiations, and the TMEM one always
 // allocates and relinquishes first thing.)
-template <bool USE_TMEM, int MIN_CTAS, int NT = VM_NT>
+// WARP_FETCH: item blocks of 32 per warp (isolated batches, see launch_program) instead of CTA-wide blocks.  A
+// template parameter, not a run-time branch: the mere presence of the second fetch path in the section loop made
+// ptxas if-convert the shared / Tensor-Memory operand loads of every opcode body (192 instead of 60 predicated
+// LDS, +5 % executed instructions, 33.1 -> 34.4 ms per wave of pairings).
+template <bool USE_TMEM, int MIN_CTAS, int NT = VM_NT, bool WARP_FETCH = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) vm_kernel(const __grid_constant__ VmParams p) {
   extern __shared__ uint4 vm_smem[];
   __shared__ uint32_t s_tmem;
@@ -347,7 +318,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) vm_kernel(const __grid_constant_
   }
   // programs without cross-thread reads: item blocks of 32 per WARP, by at most active_warps warps per CTA
   // (no block-wide barrier in the item loop; see launch_program for the balanced-waves policy)
-  const bool warp_mode = p.warp_fetch != 0 && !seg_mode;
+  constexpr bool warp_mode = WARP_FETCH;
   const bool warp_idle = warp_mode && (int)(threadIdx.x >> 5) >= p.active_warps;
   for (int phase = warp_idle ? 3 : 0; phase < 3;) {
     int lo, hi;

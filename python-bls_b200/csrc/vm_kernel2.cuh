@@ -25,9 +25,6 @@
 
 namespace b200bls {
 
-constexpr int VM2_NT_WIDE = 384;    // throughput shape: 2 CTAs of 384 threads (192 items) per SM
-constexpr int VM2_NT = 256;         // narrow shapes: 128 items per CTA, 1-3 CTAs per SM (block reductions)
-constexpr int VM2_ITEMS_PER_WARP = 16;
 
 __device__ __forceinline__ void shfl_fp(fp& x) {
 #pragma unroll
