@@ -586,11 +586,18 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
         if vid in slot_of:
             free_slots.append(slot_of.pop(vid))
         if vid in cold_of:
-            free_cold.append(cold_of.pop(vid))
+            c = cold_of.pop(vid)
+            free_cold.append(c)
+            if vid in discarded:
+                discarded.discard(vid)          # its last FILL2 already dropped the lines
+            else:
+                emit("DISCARD2", c)             # the value died in the workspace: its cold copy is dead too
+                stats["discards"] = stats.get("discards", 0) + 1
 
     marks = [None, None]
     skip_stack = []
     region_pins = set()
+    discarded = set()     # values whose cold copy the kernel has already discarded (FILL2 with aux = 1)
     for i, op in enumerate(ops):
         cur_op[0] = i
         if i == section_marks["body"]:
@@ -703,8 +710,14 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                     raise RuntimeError("fill needed inside a skip region (op %d)" % i)
                 s = alloc_slot(i, pinned)
                 slot_of[vid] = s
-                emit("FILL2", 2 * s, cold_of[vid])
+                # aux = 1: this fill serves the value's LAST use, so its cold copy is dead once it has been read --
+                # the kernel then discards the lines from the L2 instead of letting them be written back to DRAM
+                last = uses[vid][-1] == i and vid not in fixed
+                if last:
+                    discarded.add(vid)
+                emit("FILL2", 2 * s, cold_of[vid], 0, 1 if last else 0)
                 stats["fills"] += 1
+                stats["fills_last"] = stats.get("fills_last", 0) + (1 if last else 0)
         # concrete source operands
         conc = [0, 0, 0]
         for k, x in enumerate(fields):
@@ -756,7 +769,10 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                     else:
                         slot_of[r.id] = alloc_slot(i, pinned)
                 if r.id in cold_of:              # cold copy goes stale on a (partial) write
-                    free_cold.append(cold_of.pop(r.id))
+                    c = cold_of.pop(r.id)
+                    free_cold.append(c)
+                    discarded.discard(r.id)
+                    emit("DISCARD2", c)
                 conc[0] = 2 * slot_of[r.id] + (op.d.half if isinstance(op.d, Half) else 0)
         elif op.d is not None:
             conc[0] = int(op.d)

@@ -18,7 +18,7 @@ OPS = [
     ("MUL2", "c2 c2 c2", "d = a * b in Fq2"),
     ("MULXI2", "c2 c2 -", "d = a * (1 + u)"),
     ("TRI2", "c2 c2 c2", "d = 3a - 2b (aux = 0) or 3a + 2b (aux = 1)"),
-    ("FILL2", "c2 g -", "d <- cold[a]"),
+    ("FILL2", "c2 g -", "d <- cold[a]; aux = 1: last use of that cold copy (its cache lines are discarded after the read)"),
     ("SPILL2", "g c2 -", "cold[d] <- a   (global-memory spill area)"),
     ("DBL2", "c2 c2 -", "d = 2a"),
     ("NEG2", "c2 c2 -", ""),
@@ -61,6 +61,7 @@ OPS = [
     ("FLDB", "f u i", "flag[d] = (byte b of the item's record in buffer a) != 0"),
     ("INV1", "c1 c1 -", "d = 1 / a (0 -> 0): binary almost-inverse on the ALU pipe + two products"),
     ("FSQR1", "f c1 -", "flag[d] = a is a nonzero square mod q (Legendre symbol by the binary algorithm: ALU pipe only)"),
+    ("DISCARD2", "g - -", "the cold copy in slot d is dead: drop its cache lines from the L2 (no write-back to DRAM)"),
     ("END", "- - -", "end of a program section (prologue / body / epilogue): the paired kernel's interpreter loop "
                      "stops here instead of comparing its program counter with a bound it would have to keep in a register"),
 ]

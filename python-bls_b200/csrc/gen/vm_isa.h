@@ -8,7 +8,7 @@ enum VmOp : int {
   OP_MUL2 = 4,  // c2 c2 c2  d = a * b in Fq2
   OP_MULXI2 = 5,  // c2 c2 -  d = a * (1 + u)
   OP_TRI2 = 6,  // c2 c2 c2  d = 3a - 2b (aux = 0) or 3a + 2b (aux = 1)
-  OP_FILL2 = 7,  // c2 g -  d <- cold[a]
+  OP_FILL2 = 7,  // c2 g -  d <- cold[a]; aux = 1: last use of that cold copy (its cache lines are discarded after the read)
   OP_SPILL2 = 8,  // g c2 -  cold[d] <- a   (global-memory spill area)
   OP_DBL2 = 9,  // c2 c2 -  d = 2a
   OP_NEG2 = 10,  // c2 c2 -
@@ -51,12 +51,13 @@ enum VmOp : int {
   OP_FLDB = 47,  // f u i  flag[d] = (byte b of the item's record in buffer a) != 0
   OP_INV1 = 48,  // c1 c1 -  d = 1 / a (0 -> 0): binary almost-inverse on the ALU pipe + two products
   OP_FSQR1 = 49,  // f c1 -  flag[d] = a is a nonzero square mod q (Legendre symbol by the binary algorithm: ALU pipe only)
-  OP_END = 50,  // - - -  end of a program section (prologue / body / epilogue): the paired kernel's interpreter loop stops here instead of comparing its program counter with a bound it would have to keep in a register
-  OP__COUNT = 51
+  OP_DISCARD2 = 50,  // g - -  the cold copy in slot d is dead: drop its cache lines from the L2 (no write-back to DRAM)
+  OP_END = 51,  // - - -  end of a program section (prologue / body / epilogue): the paired kernel's interpreter loop stops here instead of comparing its program counter with a bound it would have to keep in a register
+  OP__COUNT = 52
 };
 // operand handling per opcode: bit0/1 load a as Fq/Fq2, bit2/3 load b as Fq/Fq2,
 // bit4/5 store the result to d as Fq/Fq2
 enum VmOpInfo : unsigned { VM_A1 = 1, VM_A2 = 2, VM_B1 = 4, VM_B2 = 8, VM_D1 = 16, VM_D2 = 32 };
-#define VM_OP_INFO_TABLE {0, 42, 42, 34, 42, 34, 42, 32, 2, 34, 34, 34, 34, 38, 21, 17, 21, 21, 17, 17, 17, 16, 32, 1, 2, 1, 5, 10, 0, 0, 0, 0, 0, 0, 0, 42, 21, 16, 16, 1, 0, 32, 2, 2, 0, 32, 0, 0, 17, 1, 0}
+#define VM_OP_INFO_TABLE {0, 42, 42, 34, 42, 34, 42, 32, 2, 34, 34, 34, 34, 38, 21, 17, 21, 21, 17, 17, 17, 16, 32, 1, 2, 1, 5, 10, 0, 0, 0, 0, 0, 0, 0, 42, 21, 16, 16, 1, 0, 32, 2, 2, 0, 32, 0, 0, 17, 1, 0, 0}
 // post-operation of the hot Fq2 producers: bits 12..14 of the destination operand, third source in aux
 enum VmPost : int { POST_NONE = 0, POST_ADD = 1, POST_SUB = 2, POST_RSUB = 3, POST_XI = 4, POST_DBL = 5, POST_SHIFT = 12 };

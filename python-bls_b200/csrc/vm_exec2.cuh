@@ -95,6 +95,9 @@ FP_DEV int vm_exec2(Env& env, uint32_t w0, uint32_t w1) {
       }
     } else if (op == OP_FILL2) {
       env.ld_cold_own(a, z);
+      env.st_own(d >> 1, z);
+      if (aux) env.discard_cold_own(a);   // after the store: the loaded registers have arrived
+      return 0;
     } else {
       env.ld_own(a >> 1, z);
       env.st_cold_own(d, z);
@@ -336,6 +339,9 @@ FP_DEV int vm_exec2(Env& env, uint32_t w0, uint32_t w1) {
       env.ld_lane_own(a >> 1, b, x);
       env.st_own(d >> 1, x);
     } break;
+    case OP_DISCARD2:
+      env.discard_cold_own(d);
+      break;
     case OP_SKIPZ:
       return env.any_flag(d) ? 0 : a;
     case OP_END:

@@ -224,6 +224,17 @@ struct DevEnv {
 #pragma unroll
     for (int k = 0; k < 3; k++) unpack(x.c1, k, __ldcg(q + (3 + k) * total));
   }
+  // The cold copy in slot g is dead (builder: FILL2 with aux = 1).  Without this every spilled value is written
+  // back to DRAM when its lines leave the L2, although nobody will read them again: discard.L2 drops the
+  // lines instead.  A 128-byte line holds the same chunk of 8 consecutive threads, all of the same warp and all
+  // at the same instruction, so one lane in eight discards it.
+  __device__ __forceinline__ void discard_cold(int g) {
+    if ((threadIdx.x & 7) == 0) {
+      const uint4* q = cold + (long long)g * 6 * total;
+#pragma unroll
+      for (int k = 0; k < 6; k++) asm volatile("discard.global.L2 [%0], 128;" ::"l"(q + k * total) : "memory");
+    }
+  }
   __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 

@@ -281,6 +281,15 @@ struct PairEnv {
 #pragma unroll
     for (int k = 0; k < 3; k++) unpack(x, k, __ldcg(q + (long long)k * total));
   }
+  // the cold copy in slot g is dead: drop its lines from the L2 instead of writing them back (vm_kernel.cuh)
+  __device__ __forceinline__ void discard_cold_own(int g) {
+    if ((threadIdx.x & 7) == 0) {
+      int total;
+      const uint4* q = cold_ptr(g, total);
+#pragma unroll
+      for (int k = 0; k < 3; k++) asm volatile("discard.global.L2 [%0], 128;" ::"l"(q + (long long)k * total) : "memory");
+    }
+  }
   __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 

@@ -132,6 +132,10 @@ struct HostEnv {
       memcpy(&x.c1.v[4 * k], coldp(g, 3 + k), 16);
     }
   }
+  void discard_cold(int g) {   // the device drops the cache lines: whatever is read from here afterwards is garbage
+    for (int k = 0; k < 6; k++)
+      for (int j = 0; j < 4; j++) coldp(g, k)[j] = 0xdeadbeefu;
+  }
   void sync() {
     std::fill(sh->written.begin(), sh->written.end(), 0);
     std::fill(sh->xread.begin(), sh->xread.end(), 0);

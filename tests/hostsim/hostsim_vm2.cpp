@@ -178,6 +178,10 @@ struct PairHostEnv {
   void ld_cold_own(int g, fp& x) {
     for (int k = 0; k < 3; k++) memcpy(&x.v[4 * k], coldp(g, k), 16);
   }
+  void discard_cold_own(int g) {   // the device drops the cache lines: a later read would see garbage
+    static const uint32_t poison[4] = {0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu};
+    for (int k = 0; k < 3; k++) put(coldp(g, k), poison);
+  }
   void sync() {
     if (sh->pass == 0) return;
     std::fill(sh->written.begin(), sh->written.end(), 0);
