@@ -539,8 +539,21 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
     out = []
     stats = {"spills": 0, "fills": 0, "max_slots": 0, "max_cold": 0}
 
+    pending = []          # dead cold slots whose lines have not been discarded yet
+
     def emit(name, d=0, a=0, b=0, aux=0):
+        # a dead cold copy rides on the next SPILL2 / FILL2 (aux = 0x80 | slot: discard that slot first) -- a
+        # stand-alone DISCARD2 costs a whole fetch / decode round, and a slot that is re-spilled at once needs none
+        if name == "SPILL2" and d in pending:
+            pending.remove(d)                           # re-spilled: the store overwrites the lines in the L2
+        if name in ("SPILL2", "FILL2") and aux == 0 and pending and not skip_stack:
+            aux = 0x80 | pending.pop(0)
         out.append((isa.OPCODE[name] | (aux << 8), d, a, b))
+
+    def flush_discards():
+        while pending:
+            c = pending.pop(0)
+            out.append((isa.OPCODE["DISCARD2"], c, 0, 0))
 
     def alloc_slot(i, pinned, smem_only=False):
         cands = [x for x in free_slots if x < n_smem] if smem_only else free_slots
@@ -590,8 +603,8 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
             free_cold.append(c)
             if vid in discarded:
                 discarded.discard(vid)          # its last FILL2 already dropped the lines
-            else:
-                emit("DISCARD2", c)             # the value died in the workspace: its cold copy is dead too
+            elif c < 0x80:
+                pending.append(c)               # the value died in the workspace: its cold copy is dead too
                 stats["discards"] = stats.get("discards", 0) + 1
 
     marks = [None, None]
@@ -601,9 +614,11 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
     for i, op in enumerate(ops):
         cur_op[0] = i
         if i == section_marks["body"]:
+            flush_discards()
             emit("END")
             marks[0] = len(out)
         if i == section_marks["epilogue"]:
+            flush_discards()
             emit("END")
             marks[1] = len(out)
         if op.name == "XCHG":
@@ -712,10 +727,10 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                 slot_of[vid] = s
                 # aux = 1: this fill serves the value's LAST use, so its cold copy is dead once it has been read --
                 # the kernel then discards the lines from the L2 instead of letting them be written back to DRAM
-                last = uses[vid][-1] == i and vid not in fixed
+                last = uses[vid][-1] == i and vid not in fixed and cold_of[vid] < 0x80
                 if last:
                     discarded.add(vid)
-                emit("FILL2", 2 * s, cold_of[vid], 0, 1 if last else 0)
+                emit("FILL2", 2 * s, cold_of[vid], 0, (0x80 | cold_of[vid]) if last else 0)
                 stats["fills"] += 1
                 stats["fills_last"] = stats.get("fills_last", 0) + (1 if last else 0)
         # concrete source operands
@@ -772,7 +787,8 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                     c = cold_of.pop(r.id)
                     free_cold.append(c)
                     discarded.discard(r.id)
-                    emit("DISCARD2", c)
+                    if c < 0x80:
+                        pending.append(c)
                 conc[0] = 2 * slot_of[r.id] + (op.d.half if isinstance(op.d, Half) else 0)
         elif op.d is not None:
             conc[0] = int(op.d)
@@ -793,11 +809,14 @@ def _assemble(prog, n_slots, n_cold, n_smem=None):
                     release(r.id)
     # every section ends with END: [prologue END | body END | epilogue END]
     if marks[0] is None:
+        flush_discards()
         emit("END")
         marks[0] = len(out)
     if marks[1] is None:
+        flush_discards()
         emit("END")
         marks[1] = len(out)
+    flush_discards()
     emit("END")
     code = np.array(out, dtype=np.uint16).reshape(-1, 4)
     stats["n_ins"] = len(out)

@@ -18,8 +18,8 @@ OPS = [
     ("MUL2", "c2 c2 c2", "d = a * b in Fq2"),
     ("MULXI2", "c2 c2 -", "d = a * (1 + u)"),
     ("TRI2", "c2 c2 c2", "d = 3a - 2b (aux = 0) or 3a + 2b (aux = 1)"),
-    ("FILL2", "c2 g -", "d <- cold[a]; aux = 1: last use of that cold copy (its cache lines are discarded after the read)"),
-    ("SPILL2", "g c2 -", "cold[d] <- a   (global-memory spill area)"),
+    ("FILL2", "c2 g -", "d <- cold[a]; aux = 0x80 | g: then drop the cache lines of the dead cold copy in slot g (g = a: this was its last use)"),
+    ("SPILL2", "g c2 -", "cold[d] <- a   (global-memory spill area); aux = 0x80 | g: first drop the lines of the dead cold copy in slot g"),
     ("DBL2", "c2 c2 -", "d = 2a"),
     ("NEG2", "c2 c2 -", ""),
     ("CONJ2", "c2 c2 -", "d = (a.c0, -a.c1)"),

@@ -8,8 +8,8 @@ enum VmOp : int {
   OP_MUL2 = 4,  // c2 c2 c2  d = a * b in Fq2
   OP_MULXI2 = 5,  // c2 c2 -  d = a * (1 + u)
   OP_TRI2 = 6,  // c2 c2 c2  d = 3a - 2b (aux = 0) or 3a + 2b (aux = 1)
-  OP_FILL2 = 7,  // c2 g -  d <- cold[a]; aux = 1: last use of that cold copy (its cache lines are discarded after the read)
-  OP_SPILL2 = 8,  // g c2 -  cold[d] <- a   (global-memory spill area)
+  OP_FILL2 = 7,  // c2 g -  d <- cold[a]; aux = 0x80 | g: then drop the cache lines of the dead cold copy in slot g (g = a: this was its last use)
+  OP_SPILL2 = 8,  // g c2 -  cold[d] <- a   (global-memory spill area); aux = 0x80 | g: first drop the lines of the dead cold copy in slot g
   OP_DBL2 = 9,  // c2 c2 -  d = 2a
   OP_NEG2 = 10,  // c2 c2 -
   OP_CONJ2 = 11,  // c2 c2 -  d = (a.c0, -a.c1)

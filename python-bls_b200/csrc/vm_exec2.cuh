@@ -96,9 +96,10 @@ FP_DEV int vm_exec2(Env& env, uint32_t w0, uint32_t w1) {
     } else if (op == OP_FILL2) {
       env.ld_cold_own(a, z);
       env.st_own(d >> 1, z);
-      if (aux) env.discard_cold_own(a);   // after the store: the loaded registers have arrived
+      if (aux & 0x80) env.discard_cold_own(aux & 0x7f);   // after the store: the loaded registers have arrived
       return 0;
     } else {
+      if (aux & 0x80) env.discard_cold_own(aux & 0x7f);   // a dead cold copy riding on this spill
       env.ld_own(a >> 1, z);
       env.st_cold_own(d, z);
       return 0;
