@@ -27,11 +27,20 @@ class Curve:
         self.prog = prog
         self.g2 = g2
         self.coord_bytes = 96 if g2 else 48
+        self._hoisted = {}
 
     def const(self, x):
+        if x in self._hoisted:
+            return self._hoisted[x]
         if self.g2:
             return self.prog.const2(x if isinstance(x, tuple) else (x, 0))
         return self.prog.const1(x)
+
+    def hoist_consts(self, *xs):
+        """load these constants once, here (call it in the prologue of a program whose body runs per item):
+        const() then hands out the same value instead of reloading it in every iteration"""
+        for x in xs:
+            self._hoisted[x] = self.const(x)
 
     def sel(self, f, a, b):
         return self.prog.sel2(f, a, b) if self.g2 else self.prog.sel1(f, a, b)
@@ -86,7 +95,7 @@ class Curve:
         z3 = (y * z).dbl()
         return (x3, y3, z3)
 
-    def add(self, p1, p2, mixed=False, inf2=None, complete=True):
+    def add(self, p1, p2, mixed=False, inf2=None, complete=True, rare_special=False):
         """Jacobian addition.  mixed=True: p2 = (x2, y2) affine with infinity flag inf2.
         complete=False leaves out the P + P case (callers whose operands cannot coincide:
         fixed-scalar ladders on points of large order); infinities and P + (-P) are still
@@ -128,6 +137,25 @@ class Curve:
                 prog.update_sel(x3, need_dbl, dx)
                 prog.update_sel(y3, need_dbl, dy)
                 prog.update_sel(z3, need_dbl, dz)
+        if rare_special:
+            # P + (-P) and infinite operands patched in place inside ONE region that a warp skips unless a lane
+            # needs it (the per-point folds: seven selects less on the common path)
+            special = opposite | inf1 | inf2
+            zero, one = self.const(0), self.const(1)
+            with prog.skip_unless(special):
+                prog.update_sel(z3, opposite, zero)
+                if mixed:
+                    z2j = self.sel(inf2, zero, one)
+                    p2j = (x2, y2, z2j)
+                else:
+                    p2j = p2
+                prog.update_sel(x3, inf1, p2j[0])
+                prog.update_sel(y3, inf1, p2j[1])
+                prog.update_sel(z3, inf1, p2j[2])
+                prog.update_sel(x3, inf2, x1)
+                prog.update_sel(y3, inf2, y1)
+                prog.update_sel(z3, inf2, z1)
+            return (x3, y3, z3)
         # P + (-P) = infinity (Z = 0; X, Y arbitrary non-garbage)
         z3 = self.sel(opposite, self.const(0), z3)
         # identity operands
@@ -256,6 +284,7 @@ def build_sum_pass1(g2):
     def build():
         prog = Program("g2_sum1" if g2 else "g1_sum1")
         c = Curve(prog, g2)
+        c.hoist_consts(0, 1)
         inf0 = c.infinity()
         acc = [prog.var2(v) if g2 else v for v in inf0]
         if not g2:
@@ -265,7 +294,7 @@ def build_sum_pass1(g2):
         x, y, inf = c.load_affine(0)
         inf = inf | ~prog.flag_active()
         cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
-        s = c.add(cur, (x, y), mixed=True, inf2=inf)
+        s = c.add(cur, (x, y), mixed=True, inf2=inf, rare_special=True)
         for a, v in zip(acc, s):
             if g2:
                 prog.assign(a, v)

@@ -474,24 +474,6 @@ FP_DEV void fp_mul_inline(fp& r, const fp& a, const fp& b) {
 // 2^32 (a + b + q) < 2^416 (5q = 0.51 R), the result below 8 q^2 / R + q = 1.82 q: weakly reduced
 // without a final subtraction.
 // ---------------------------------------------------------------------------------------
-FP_DEV void mont_round2_first(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t xi, const uint32_t* b,
-                              uint32_t yi) {
-#pragma unroll
-  for (int j = 0; j < NL; j += 2) {
-    ev[j] = mul_lo(a[j], xi);
-    ev[j + 1] = mul_hi(a[j], xi);
-    od[j] = mul_lo(a[j + 1], xi);
-    od[j + 1] = mul_hi(a[j + 1], xi);
-  }
-  mad_row<false>(od, b + 1, yi);  // no carry out of the odd set: T < 2^(32*13)
-  mad_row<false>(ev, b, yi);
-  od[NL - 1] = addc(od[NL - 1], 0);
-  uint32_t m = mul_lo(ev[0], Q_INV_NEG);
-  mad_row_q<1>(od, m);
-  mad_row_q<0>(ev, m);
-  od[NL - 1] = addc(od[NL - 1], 0);
-}
-
 FP_DEV void mont_round2(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t xi, const uint32_t* b, uint32_t yi) {
   ev[0] = add_cc(ev[0], od[1]);
   madc_row_rshift(od, a + 1, xi);
@@ -515,35 +497,17 @@ FP_DEV void mont_finish(fp& r, const uint32_t* ev, const uint32_t* od) {
 }
 
 // x, y arrive four words at a time (the streaming form: the kernel loads one 16-byte chunk of each
-// per four rounds, so only a and b are held in registers for the whole product)
+// per four rounds, so only a and b are held in registers for the whole product); the accumulators
+// start at zero, so that every round is the general one and the twelve rounds are a loop of three passes
 struct Mul2State {
   uint32_t ev[NL], od[NL];
 };
-template <int K>
-FP_DEV void fp_mul2_chunk(Mul2State& s, const fp& a, const fp& b, const uint32_t* x4, const uint32_t* y4) {
-  if (K == 0)
-    mont_round2_first(s.ev, s.od, a.v, x4[0], b.v, y4[0]);
-  else
-    mont_round2(s.ev, s.od, a.v, x4[0], b.v, y4[0]);
-  mont_round2(s.od, s.ev, a.v, x4[1], b.v, y4[1]);
-  mont_round2(s.ev, s.od, a.v, x4[2], b.v, y4[2]);
-  mont_round2(s.od, s.ev, a.v, x4[3], b.v, y4[3]);
-}
-
 // four general rounds (accumulators may start at zero): the body of the looped streaming product
 FP_DEV void fp_mul2_rounds4(Mul2State& s, const fp& a, const fp& b, const uint32_t* x4, const uint32_t* y4) {
   mont_round2(s.ev, s.od, a.v, x4[0], b.v, y4[0]);
   mont_round2(s.od, s.ev, a.v, x4[1], b.v, y4[1]);
   mont_round2(s.ev, s.od, a.v, x4[2], b.v, y4[2]);
   mont_round2(s.od, s.ev, a.v, x4[3], b.v, y4[3]);
-}
-
-FP_DEV void fp_mul2_inline(fp& r, const fp& a, const fp& x, const fp& b, const fp& y) {
-  Mul2State s;
-  fp_mul2_chunk<0>(s, a, b, x.v, y.v);
-  fp_mul2_chunk<1>(s, a, b, x.v + 4, y.v + 4);
-  fp_mul2_chunk<2>(s, a, b, x.v + 8, y.v + 8);
-  mont_finish(r, s.ev, s.od);
 }
 
 // The twelve rounds as a LOOP of three passes over four rounds (b rotates down four limbs per pass, the

@@ -2,15 +2,16 @@
 // batch item (vm_exec2.cuh): thread pair (2i, 2i + 1) of a warp owns item i of the warp's block of
 // 16 items, thread `role` owning coefficient `role` of every Fq2 slot.
 //
-// Per-item resources are those of the one-thread-per-item design (vm_kernel.cuh, kept for the host
-// simulation's reference semantics): `n_slots` Fq2 slots in shared memory, laid out
+// Per-item resources are those of the one-thread-per-item kernel (vm_kernel.cuh, the throughput
+// kernel): `n_slots` Fq2 slots in shared memory, laid out
 // [slot][16-byte chunk 0..2][thread] so that a warp's LDS.128 / STS.128 covers 512 contiguous bytes
 // (own column) or the same 512 bytes permuted within pairs (partner's column): conflict free;
 // `n_tmem` slots in Tensor Memory (12 columns per slot and thread, lanes private); spills to the
-// L2-backed cold area [cold slot][chunk][global thread].  What doubles is the number of warps: the
-// throughput shape is 2 CTAs x 384 threads = 24 warps per SM on <= 80 registers, where the
-// one-thread design held 12 warps on 146 -- three warps per scheduler could not keep the quarter-rate
-// IMAD.WIDE pipe full (81 % in round 1), six can.
+// L2-backed cold area [cold slot][chunk][global thread].  What doubles is the number of warps (2 CTAs x
+// 384 threads = 24 warps per SM on <= 80 registers, against 12 warps on 146) and what halves is the
+// work per thread.  Measured: 0.81x the throughput of the one-thread kernel --
+// decode, dispatch and operand addressing are paid per thread -- but 0.70x the latency of an isolated
+// pass, so the launcher sends small isolated batches here.
 //
 // Work distribution: programs without cross-thread reads hand out blocks of 16 items PER WARP from a
 // global counter -- no block-wide barrier in the item loop, a warp that finds no work left is done,
@@ -31,7 +32,7 @@ __device__ __forceinline__ void shfl_fp(fp& x) {
   for (int i = 0; i < NL; i++) x.v[i] = __shfl_xor_sync(0xffffffffu, x.v[i], 1);
 }
 
-// The streaming two-row product (fp.cuh: fp_mul2_chunk): a and b stay in registers, the other two
+// The streaming two-row product (fp.cuh: fp_mul2_rounds4): a and b stay in registers, the other two
 // operands -- the two coefficients of one workspace slot -- arrive one 16-byte chunk per four
 // rounds: from the own and the partner's shared-memory column, or, for a Tensor-Memory slot, from
 // the own lane plus a shuffle.  One copy in the kernel (the hot code has to fit the instruction
