@@ -9,10 +9,13 @@ from . import curve, extras, fieldops, hashg2, pairing
 # program cannot use TMEM (cross-thread reads) the shared-memory-only shape is used, and when
 # it does not fit a shape at all the launcher falls back to fewer CTAs per SM.
 N_SLOTS = 18
-SHAPES = {1: (18, 21), 2: (9, 10), 3: (6, 5), 4: (6, 7)}
+SHAPES = {1: (18, 21), 2: (9, 10), 3: (6, 5), 4: (6, 7), 5: (4, 5)}
 # Shape 4 is the "wide" shape: ONE CTA of 384 threads per SM (same 12 warps as shape 3) that owns all
 # 512 TMEM columns, 168 per group of four warps = 7 slots instead of 5.  TMEM programs only.
-WIDE_SHAPES = {4}
+# Shape 5 is ONE CTA of 512 threads per SM (16 warps, 128 registers): 4 + 5 slots per item, more spills, but
+# 75,776 items in one pass -- the shape of an isolated batch that is a little more than one 384-thread wave
+# (BASELINE config 2: 65,536 pairings = 1.15 waves of shape 4, 0.86 of shape 5).
+WIDE_SHAPES = {4, 5}
 if os.environ.get("B200BLS_SHAPES"):          # experiments: "ctas:smem_slots:tmem_slots,..."
     SHAPES = {int(c): (int(a), int(b)) for c, a, b in
               (item.split(":") for item in os.environ["B200BLS_SHAPES"].split(","))}

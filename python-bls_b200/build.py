@@ -45,7 +45,7 @@ def build(force=False, verbose=True):
     if force or _newer(blob_o, [blob]):
         subprocess.check_call(["ld", "-r", "-b", "binary", "-z", "noexecstack", "-o", "programs_blob.o",
                                "programs.bin"], cwd=GEN)
-    srcs = [os.path.join(CSRC, f) for f in ("b200bls.cu", "kernel1.cu", "kernel2.cu", "microbench.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("b200bls.cu", "kernel1.cu", "kernel2.cu", "kernel3.cu", "microbench.cu")]
     deps = srcs + _walk(CSRC, (".cuh", ".h")) + [blob_o, os.path.join(ROOT, "include", "b200bls.h")]
     if force or _newer(LIB, deps):
         cmd = ["nvcc"] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + [blob_o, "-ldl", "-lrt"]

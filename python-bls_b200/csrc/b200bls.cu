@@ -102,6 +102,7 @@ struct Context {
   // 20.0 ms for up to 9,472 pairings); 0 = choose per launch: the paired kernel for isolated batches that leave
   // most of the GPU empty, the one-thread kernel otherwise.  Environment variable B200BLS_KERNEL.
   int kernel = 0;
+  int isolated_shape = 0;   // experiments: B200BLS_ISOLATED_SHAPE forces the shape of automatic (isolated) launches
 };
 
 Context g_ctx;
@@ -142,7 +143,7 @@ int launch_program2(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int
 int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int n_bufs, int grid_override = 0,
                    const SegArgs* seg = nullptr) {
   Context& c = g_ctx;
-  if (c.kernel == 2) return launch_program2(pr, n_items, bufs, n_bufs, grid_override, seg);
+  if (c.kernel == 2 && pr.ctas2 > 0) return launch_program2(pr, n_items, bufs, n_bufs, grid_override, seg);
   // automatic: latency-bound launches (at most one 128-item block per SM, no block reduction) go to the paired kernel
   if (c.kernel == 0 && c.ctas_per_sm == 0 && grid_override == 0 && !seg && !pr.cross_thread &&
       n_items <= (size_t)c.sm_count * 128)
@@ -210,7 +211,13 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
   p.smem_cells = 2 * pr.n_slots;
   for (int i = 0; i < n_bufs && i < VM_MAX_BUFS; i++) p.bufs[i] = bufs[i];
   size_t smem = (size_t)pr.n_slots * 2 * 3 * sizeof(uint4) * nt;
-  if (nt == VM_NT_WIDE) {
+  if (nt == VM_NT_XWIDE) {
+    // four groups of four warps: 128 columns each (5 Fq2 slots)
+    if (pr.n_tmem * 24 > 128) return fail(B200BLS_E_PROGRAM, "shape 5: %d TMEM slots do not fit 128 columns", pr.n_tmem);
+    p.tmem_cols = 512;
+    p.tmem_group_cols = 128;
+    vm3_launch(grid, smem, sc.stream, p);
+  } else if (nt == VM_NT_WIDE) {
     // three groups of four warps share the SM's 512 columns: 168 each (7 Fq2 slots)
     if (pr.n_tmem * 24 > 168) return fail(B200BLS_E_PROGRAM, "wide shape: %d TMEM slots do not fit 168 columns", pr.n_tmem);
     p.tmem_cols = 512;
@@ -333,6 +340,14 @@ const DevProgram* find_program(const char* base, size_t n_items = 0) {
     int want = g_ctx.ctas_per_sm > 0 ? g_ctx.ctas_per_sm : auto_ctas(n_items ? n_items : 1);
     // the wide shape (id 4) holds as many items per SM as three narrow CTAs and is faster where it exists
     if (g_ctx.ctas_per_sm == 0 && want == 3) want = 4;
+    if (g_ctx.ctas_per_sm == 0 && g_ctx.kernel != 2) {
+      // an isolated batch that is a little more than whole 384-item waves: fewer passes on the 512-thread shape
+      const size_t sm = (size_t)g_ctx.sm_count, n = n_items ? n_items : 1;
+      const size_t p16 = (n + sm * VM_NT_XWIDE - 1) / (sm * VM_NT_XWIDE), p12 = (n + sm * VM_NT_WIDE - 1) / (sm * VM_NT_WIDE);
+      if (n > sm * VM_NT && p16 < p12) want = 5;
+      if (g_ctx.isolated_shape > 0 && n > sm * VM_NT) want = g_ctx.isolated_shape;
+    }
+    if (want == 5 && g_ctx.kernel == 2) want = 4;   // the paired kernel has no 512-thread shape
     for (int c = want; c >= 1; c--) {
       auto it = g_ctx.programs.find(name + "@" + std::to_string(c));
       if (it != g_ctx.programs.end()) return &it->second;
@@ -833,6 +848,7 @@ int b200bls_init(int device) {
   CU(cudaEventCreate(&c.ev1));
   CU(vm1_configure());
   CU(vm2_configure());
+  CU(vm3_configure());
   // parse the embedded program blob
   const unsigned char* blob = _binary_programs_bin_start;
   size_t blob_len = (size_t)(_binary_programs_bin_end - _binary_programs_bin_start);
@@ -859,6 +875,10 @@ int b200bls_init(int device) {
       dp.threads = VM_NT_WIDE;
       dp.ctas2 = 2;
       dp.items = VM2_NT_WIDE / 2;
+    } else if (dp.ctas == 5) {  // shape id 5: one CTA of 512 threads (one-thread kernel only)
+      dp.ctas = 1;
+      dp.threads = VM_NT_XWIDE;
+      dp.ctas2 = 0;
     }
     {
       const unsigned char* code = blob + en.code_off;
@@ -883,7 +903,9 @@ int b200bls_init(int device) {
   const char* kenv = getenv("B200BLS_KERNEL");
   if (kenv && kenv[0] >= '0' && kenv[0] <= '2') c.kernel = kenv[0] - '0';
   const char* env = getenv("B200BLS_CTAS_PER_SM");
-  if (env && env[0] >= '0' && env[0] <= '4') c.ctas_per_sm = env[0] - '0';
+  if (env && env[0] >= '0' && env[0] <= '5') c.ctas_per_sm = env[0] - '0';
+  const char* ienv = getenv("B200BLS_ISOLATED_SHAPE");
+  c.isolated_shape = (ienv && ienv[0] >= '1' && ienv[0] <= '5') ? ienv[0] - '0' : 0;
   c.device = device;
   c.ready = true;
   return 0;
@@ -927,8 +949,8 @@ int b200bls_sm_count(void) { return g_ctx.ready ? g_ctx.sm_count : 0; }
 
 int b200bls_set_ctas_per_sm(int n) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (n < 0 || n > 4)
-    return fail(B200BLS_E_ARG, "ctas_per_sm must be 0 (auto), 1, 2, 3 or 4 (one wide CTA of 384 threads)");
+  if (n < 0 || n > 5)
+    return fail(B200BLS_E_ARG, "ctas_per_sm must be 0 (auto), 1, 2, 3, 4 (one CTA of 384 threads) or 5 (one of 512)");
   g_ctx.ctas_per_sm = n;
   return 0;
 }

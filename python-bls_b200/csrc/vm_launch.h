@@ -11,6 +11,8 @@
 namespace b200bls {
 cudaError_t vm1_configure();
 void vm1_launch(bool use_tmem, bool wide, int grid, size_t smem, cudaStream_t stream, const VmParams& p);
+cudaError_t vm3_configure();   // kernel3.cu: the one-thread kernel at 512 threads per CTA (its own 128-register budget)
+void vm3_launch(int grid, size_t smem, cudaStream_t stream, const VmParams& p);
 cudaError_t vm2_configure();
 void vm2_launch(bool use_tmem, bool wide, bool seg, int grid, size_t smem, cudaStream_t stream, const VmParams& p);
 }  // namespace b200bls

@@ -9,6 +9,8 @@ constexpr int VM_NT = 128;      // threads per CTA (default shapes)
 constexpr int VM_NT_WIDE = 384; // "wide" shape: ONE CTA of 12 warps per SM.  Three 128-thread CTAs can only
                                 // allocate 128 TMEM columns each (power-of-two allocations, 512 per SM); one CTA
                                 // owns all 512 and gives each group of four warps 168 columns = 7 Fq2 slots
+constexpr int VM_NT_XWIDE = 512; // shape 5: ONE CTA of 16 warps per SM (128 registers per thread), 128 TMEM columns per group of four
+                                 // warps = 5 Fq2 slots, 4 slots of shared memory
 constexpr int VM_MAX_BUFS = 8;
 
 struct VmBuf {

@@ -76,9 +76,9 @@ def test_scalar_mul_small_order_and_off_subgroup_points():
             assert out[w * i:w * (i + 1)] == (bytes(w) if want[2] else ser(want)), (g2, i)
 
 
-@pytest.mark.parametrize("ctas", [1, 2, 3, 4])
+@pytest.mark.parametrize("ctas", [1, 2, 3, 4, 5])
 def test_ragged_batches_every_shape(ctas):
-    """batch sizes around the CTA (128, or 384 for the wide shape 4) and wave boundaries, one known
+    """batch sizes around the CTA (128, 384 for the wide shape 4, 512 for shape 5) and wave boundaries, one known
     pairing repeated"""
     from bls_b200 import _lib, engine
     _lib.init()
@@ -86,8 +86,8 @@ def test_ragged_batches_every_shape(ctas):
     try:
         p, q = O.aff_mul(9, O.G1), O.aff_mul(4, O.G2)
         want = O.f12_serialize(O.ate_pairing(p, q))
-        wave = _lib.lib.b200bls_sm_count() * 128 * min(ctas, 3)
-        for n in (1, 127, 129, 383, 385, wave - 1, wave + 1):
+        wave = _lib.lib.b200bls_sm_count() * 128 * {4: 3, 5: 4}.get(ctas, ctas)
+        for n in (1, 127, 129, 383, 385, 511, 513, wave - 1, wave + 1):
             out = engine.pairing_batch(ser1(p) * n, ser2(q) * n).tobytes()
             assert out[:576] == want and out[-576:] == want
             assert out == want * n
@@ -127,7 +127,7 @@ def test_every_launch_shape_gives_the_same_bytes():
     g1 = np.frombuffer(ser1(O.G1), dtype=np.uint8)
     results = []
     try:
-        for ctas in (1, 2, 3, 4):
+        for ctas in (1, 2, 3, 4, 5):
             _lib.check(_lib.lib.b200bls_set_ctas_per_sm(ctas))
             H = engine.hash_to_g2(hs)
             sig = engine.scalar_mul(H, sc, True)
