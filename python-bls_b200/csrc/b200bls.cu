@@ -461,8 +461,8 @@ int sum_dev(bool g2, const void* pts, void* out, size_t n) {
 // 217-221): bucket method.  Scalars are cut into MSM_W windows of MSM_C bits; a counting sort
 // groups the (point, window) pairs by bucket = (window, digit); buckets are cut into segments
 // of bounded length and one thread per segment folds its points (g?_bucket program, segmented
-// launch); the segment sums are then multiplied by digit << (MSM_C * window) with the ordinary
-// scalar-multiplication program and summed by the ordinary reduction.  24 mixed additions per
+// launch); the segment sums are then multiplied by digit << (MSM_C * window) -- an MSM_C-bit ladder and `window`
+// blocks of MSM_C doublings, warp-uniformly skipped (g?_bscale) -- and summed by the ordinary reduction.  24 mixed additions per
 // point instead of 255 doublings + ~128 additions.
 constexpr int MSM_C = 11;
 constexpr int MSM_W = 24;                  // 24 * 11 = 264 >= 256 bits
@@ -530,21 +530,23 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(unsigned* __restrict__ c
   }
 }
 
-// segment table: seg_start[s] = first position of segment s in the index list, seg_scalar[s] =
-// digit << (MSM_C * window) of its bucket as 32 big-endian bytes.  One thread per bucket.
+// segment table: seg_start[s] = first position of segment s in the index list, seg_scalar[s] = the bucket's scalar
+// digit << (MSM_C * window) as a 32-byte record {digit: 2 bytes big-endian, g[k] = (window > k) for k < MSM_W - 1}.
+// One thread per bucket.
 __global__ void msm_segments_kernel(const unsigned* __restrict__ start, const unsigned* __restrict__ seg_first,
                                     unsigned seg_len, unsigned* __restrict__ seg_start, uint8_t* __restrict__ seg_scalar) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= MSM_B) return;
   const unsigned s0 = seg_first[b], s1 = seg_first[b + 1];
-  const int w = b >> MSM_C, lo = w * MSM_C;
-  const unsigned long long d = (unsigned long long)(b & ((1 << MSM_C) - 1)) << (lo & 7);
+  const int w = b >> MSM_C;
+  const unsigned d = (unsigned)(b & ((1 << MSM_C) - 1));
   for (unsigned s = s0; s < s1; s++) {
     seg_start[s] = start[b] + (s - s0) * seg_len;
+    // the record the g?_bscale program reads (programs/curve.py: build_bucket_scale)
     uint8_t* o = seg_scalar + (size_t)s * 32;
-    for (int k = 0; k < 32; k++) o[k] = 0;
-    for (int k = 0; k < 3; k++)
-      if ((lo >> 3) + k < 32) o[31 - ((lo >> 3) + k)] = (uint8_t)(d >> (8 * k));
+    o[0] = (uint8_t)(d >> 8);
+    o[1] = (uint8_t)d;
+    for (int k = 0; k < 30; k++) o[2 + k] = (k < MSM_W - 1 && w > k) ? 1 : 0;
   }
   if (b == MSM_B - 1) seg_start[s1] = start[MSM_B];
 }
@@ -615,7 +617,7 @@ int msm_dev(bool g2, const void* pts, const void* scalars, void* out, size_t n) 
   rc = launch_program(*fold, n_seg, bf, 2, 0, &seg);
   if (rc) return rc;
   VmBuf bm[3] = {vb(sc.scratch[6].ptr, (long long)w), vb(seg_scalar, 32), vb(sc.scratch[11].ptr, (long long)w)};
-  rc = launch_named(mul, n_seg, bm, 3);
+  rc = launch_named(g2 ? "g2_bscale" : "g1_bscale", n_seg, bm, 3);
   if (rc) return rc;
   return sum_dev(g2, sc.scratch[11].ptr, out, n_seg);
 }

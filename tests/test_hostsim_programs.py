@@ -231,6 +231,42 @@ def test_windowed_scalar_mul_program(g2):
         assert raw[w * i:w * (i + 1)] == ser(want), (g2, i, k)
 
 
+@pytest.mark.parametrize("g2", [False, True])
+def test_bucket_scale_program(g2):
+    """(digit << 11 w) * P of the multi-scalar multiplication's bucket sums (programs/curve.py: build_bucket_scale):
+    digits 0, 1, 2047 and mixed, windows 0, 1, 23, mixed windows inside one block of lanes (the skip regions must be
+    no-ops for the lanes that do not take them), infinity and the order-3 point"""
+    G = O.G2 if g2 else O.G1
+    w = 192 if g2 else 96
+
+    def ser(p):
+        if p[2]:
+            return bytes(w)
+        if g2:
+            return b"".join(c.to_bytes(48, "big") for c in (p[0][0], p[0][1], p[1][0], p[1][1]))
+        return p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+
+    inf = (G[0], G[1], True)
+    base = (G[0], G[1], False)
+    cases = [(base, 1, 0), (base, 0, 5), (base, 2047, 0), (base, 1365, 23), (base, 3, 1), (inf, 77, 3), (base, 1024, 11),
+             (O.aff_mul(7, G), 682, 22), (base, 1, 23)]
+    if not g2:
+        cases += [((0, 2, False), 1, 0), ((0, 2, False), 2, 1), ((0, 2, False), 3, 2)]
+    asm = curve.build_bucket_scale(g2)().assemble(6, n_cold=4096, n_tmem=7)
+    P = np.frombuffer(b"".join(ser(p) for p, _, _ in cases), dtype=np.uint8).copy()
+    rec = bytearray()
+    for _, d, win in cases:
+        rec += d.to_bytes(2, "big") + bytes(1 if win > k else 0 for k in range(curve.MSM_W - 1)) + bytes(32 - 2 - (curve.MSM_W - 1))
+    S = np.frombuffer(bytes(rec), dtype=np.uint8).copy()
+    out = np.zeros(w * len(cases), dtype=np.uint8)
+    hostsim.run(asm, {0: P, 1: S, 2: out}, {0: w, 1: 32, 2: w}, len(cases), n_blocks=3, nt=4)
+    raw = out.tobytes()
+    for i, (p, d, win) in enumerate(cases):
+        k = d << (curve.MSM_C * win)
+        want = O.to_aff(O.jac_mul(k, O.to_jac(p))) if not p[2] else (0, 0, True)
+        assert raw[w * i:w * (i + 1)] == ser(want), (g2, i, d, win)
+
+
 def test_instruction_fusion_patterns():
     """builder.fuse_pairs: every post-operation (z+c, z-c, c-z, xi*z, 2z) behind every primary, on the
     host build of the device code against plain modular arithmetic; and the cases that must NOT fuse
