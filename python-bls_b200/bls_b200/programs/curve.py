@@ -382,14 +382,33 @@ def build_sum_pass2(g2):
     return build
 
 
-def build_bucket_fold(g2):
+def build_to_mont(g2):
+    """buffers: 0 = affine points (big-endian bytes), 1 = the same coordinates as raw Montgomery limbs (SoA, one Fq2
+    cell per item and element: G2 x, y; G1 (x, y) packed).  The multi-scalar multiplication reads every point once per
+    window (24 times): converting once here takes the byte swap and the to-Montgomery product out of its fold."""
+    def build():
+        prog = Program("g2_tomont" if g2 else "g1_tomont")
+        prog.begin_body()
+        c = Curve(prog, g2)
+        x = c.load(0, 0)
+        y = c.load(0, c.coord_bytes)
+        if g2:
+            prog.store_raw2(1, 0, x)
+            prog.store_raw2(1, 1, y)
+        else:
+            prog.store_raw2(1, 0, prog.pack(x, y))
+        return prog
+    return build
+
+
+def build_bucket_fold(g2, raw=False):
     """One bucket of the multi-scalar multiplication per thread (segmented launch mode of the
-    kernel): buffers 0 = affine points, read through the sorted index list, 1 = out, one affine
-    bucket sum per thread.  The accumulator stays Jacobian across the segment; one inversion per
-    bucket at the end.  Used by secure aggregation, sum_i T_i * P_i (bls_py/bls.py:29-56,
+    kernel): buffers 0 = affine points, read through the sorted index list (raw=True: the Montgomery-form copy
+    written by g?_tomont), 1 = out, one affine bucket sum per thread.  The accumulator stays Jacobian across the
+    segment; one inversion per bucket at the end.  Used by secure aggregation, sum_i T_i * P_i (bls_py/bls.py:29-56,
     132-144, 217-221)."""
     def build():
-        prog = Program("g2_bucket" if g2 else "g1_bucket")
+        prog = Program(("g2_bucket" if g2 else "g1_bucket") + ("r" if raw else ""))
         c = Curve(prog, g2)
         inf0 = c.infinity()
         if g2:
@@ -397,7 +416,15 @@ def build_bucket_fold(g2):
         else:
             acc = [prog.var2(prog.pack(v, v)) for v in inf0]
         prog.begin_body()
-        x, y, inf = c.load_affine(0)
+        if not raw:
+            x, y, inf = c.load_affine(0)
+        elif g2:
+            x, y = prog.load_raw2(0, 0), prog.load_raw2(0, 1)
+            inf = x.is_zero() & y.is_zero()
+        else:
+            xy = prog.load_raw2(0, 0)
+            x, y = xy.c0, xy.c1
+            inf = x.is_zero() & y.is_zero()
         inf = inf | ~prog.flag_active()
         cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
         s = c.add(cur, (x, y), mixed=True, inf2=inf)

@@ -58,6 +58,8 @@ for _g2 in (False, True):
     PROGRAMS[_p + "_sum2"] = curve.build_sum_pass2(_g2)
     PROGRAMS[_p + "_bucket"] = curve.build_bucket_fold(_g2)
     PROGRAMS[_p + "_bscale"] = curve.build_bucket_scale(_g2)
+    PROGRAMS[_p + "_tomont"] = curve.build_to_mont(_g2)
+    PROGRAMS[_p + "_bucketr"] = curve.build_bucket_fold(_g2, raw=True)
     PROGRAMS[_p + "_decompress"] = curve.build_decompress(_g2)
     for _op in ("affine", "dbl", "add", "mul"):        # the plugin seam's Jacobian-coordinate functions
         PROGRAMS[_p + "_j" + _op] = curve.build_jacobian_op(_g2, _op)

@@ -610,10 +610,16 @@ int msm_dev(bool g2, const void* pts, const void* scalars, void* out, size_t n) 
   CU(cudaStreamSynchronize(STREAM));
   if (n_seg == 0) return sum_dev(g2, pts, out, 0);  // every scalar is zero
   if (n_seg > seg_cap) return fail(B200BLS_E_CUDA, "msm: segment count %u exceeds its bound %zu", n_seg, seg_cap);
-  const DevProgram* fold = find_program(g2 ? "g2_bucket" : "g1_bucket", n_seg);
+  // every point is read once per window: convert it to Montgomery limbs once (SoA copy), not MSM_W times in the fold
+  rc = ensure_scratch(4, w * n);
+  if (rc) return rc;
+  VmBuf bt[2] = {vb(pts, (long long)w), vb(sc.scratch[4].ptr, (long long)n)};
+  rc = launch_named(g2 ? "g2_tomont" : "g1_tomont", n, bt, 2);
+  if (rc) return rc;
+  const DevProgram* fold = find_program(g2 ? "g2_bucketr" : "g1_bucketr", n_seg);
   if (!fold) return B200BLS_E_PROGRAM;
   SegArgs seg = {seg_start, idx};
-  VmBuf bf[2] = {vb(pts, (long long)w), vb(sc.scratch[6].ptr, (long long)w)};
+  VmBuf bf[2] = {vb(sc.scratch[4].ptr, (long long)n), vb(sc.scratch[6].ptr, (long long)w)};
   rc = launch_program(*fold, n_seg, bf, 2, 0, &seg);
   if (rc) return rc;
   VmBuf bm[3] = {vb(sc.scratch[6].ptr, (long long)w), vb(seg_scalar, 32), vb(sc.scratch[11].ptr, (long long)w)};
