@@ -60,7 +60,10 @@ int b200bls_stream_count(void);
  * per thread), 2 (9 + 10) or 3 (6 + 5); 4 = the "wide" shape, ONE CTA of 384 threads per SM that
  * owns all 512 Tensor-Memory columns (6 + 7 slots per thread; programs without block-level
  * reductions only, the others fall back to 3).  More warps per SM = more throughput, but a
- * longer single pass.  0 (default, or environment variable B200BLS_CTAS_PER_SM) chooses per call
+ * longer single pass.  5 = ONE CTA of 512 threads per SM (16 warps, 4 + 5 slots per thread): 0.97x
+ * the throughput of 4 on whole waves, but 75,776 items in one pass -- what the automatic choice
+ * takes for an isolated batch that is a little more than whole 384-item waves (65,536 pairings).
+ * 0 (default, or environment variable B200BLS_CTAS_PER_SM) chooses per call
  * the shape that finishes an isolated batch soonest; pipelines that keep batches in flight on
  * several streams should select 4. */
 int b200bls_set_ctas_per_sm(int n);

@@ -350,6 +350,69 @@ def build_sum_pass1(g2):
     return build
 
 
+def build_sum_fold(g2):
+    """Large sums, pass A: buffers 0 = affine points (n items), 1 = raw SoA Jacobian partials, ONE PER THREAD.  No
+    cross-thread step, so the program runs in the 12-warp shape with Tensor-Memory slots (g?_sum1 with its CTA
+    tree is held to two CTAs of 128 threads per SM); pass B (g?_sum1j) folds and tree-reduces the partials."""
+    def build():
+        prog = Program("g2_sumf" if g2 else "g1_sumf")
+        c = Curve(prog, g2)
+        inf0 = c.infinity()
+        if g2:
+            acc = [prog.var2(v) for v in inf0]
+        else:
+            acc = [prog.var2(prog.pack(v, v)) for v in inf0]
+        prog.begin_body()
+        x, y, inf = c.load_affine(0)
+        inf = inf | ~prog.flag_active()
+        cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
+        s = c.add(cur, (x, y), mixed=True, inf2=inf)
+        for a, v in zip(acc, s):
+            if g2:
+                prog.assign(a, v)
+            else:
+                prog.emit("MOV1", a.c0, v)
+        prog.begin_epilogue()
+        cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
+        for k, v in enumerate(_pack_point(prog, c, cur)):
+            prog.store_raw2(1, k, v)
+        return prog
+    return build
+
+
+def build_sum_pass1j(g2):
+    """Large sums, pass B: buffers 0 = raw SoA Jacobian partials (n items, one per thread of pass A), 1 = raw SoA
+    partials, one per CTA.  Full Jacobian additions per thread, then the CTA tree of g?_sum1."""
+    def build():
+        prog = Program("g2_sum1j" if g2 else "g1_sum1j")
+        c = Curve(prog, g2)
+        inf0 = c.infinity()
+        if g2:
+            acc = [prog.var2(v) for v in inf0]
+        else:
+            acc = [prog.var2(prog.pack(v, v)) for v in inf0]
+        prog.begin_body()
+        n_vals = 3 if g2 else 2
+        vals = [prog.load_raw2(0, k) for k in range(n_vals)]
+        p = _unpack_point(prog, c, vals)
+        act = prog.flag_active()
+        p = (p[0], p[1], c.sel(act, p[2], c.const(0)))
+        cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
+        s = c.add(cur, p)
+        for a, v in zip(acc, s):
+            if g2:
+                prog.assign(a, v)
+            else:
+                prog.emit("MOV1", a.c0, v)
+        prog.begin_epilogue()
+        cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
+        tot = _tree_reduce(prog, c, cur)
+        for k, v in enumerate(_pack_point(prog, c, tot)):
+            prog.store_raw2(1, k, v, block_only=True)
+        return prog
+    return build
+
+
 def build_sum_pass2(g2):
     """buffers: 0 = raw SoA partials (n items, one per CTA of pass 1), 1 = out (affine, one
     point).  Launched with a single CTA."""

@@ -383,6 +383,9 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) vm_kernel(const __grid_constant_
       lo = p.epi_start;
       hi = p.n_ins;
       phase = 3;
+      // the epilogue addresses the thread's own record (per-thread partials of g?_sumf), as in segmented mode
+      env.item_raw = gtid;
+      env.item = gtid < last ? gtid : last;
     }
     vm_run_section(env, p.code, lo, hi);
   }

@@ -194,7 +194,7 @@ extern "C" int hs_vm_run(const uint32_t* code, int n_ins, int body_start, int ep
   };
   run(0, body_start, 0);
   for (long it = 0; it < iters; it++) run(body_start, epi_start, it);
-  run(epi_start, n_ins, iters > 0 ? iters - 1 : 0);
+  run(epi_start, n_ins, 0);  // the epilogue addresses the thread's own record: item_raw = global thread id
   return 0;
 }
 
