@@ -187,7 +187,9 @@ int launch_program(const DevProgram& pr, size_t n_items, const VmBuf* bufs, int 
     p.seg_start = seg->start;
     p.seg_idx = seg->idx;
   }
-  if (!pr.cross_thread && !seg && c.ctas_per_sm == 0 && grid_override == 0) {
+  // (not for shape 5: with 16 warps per CTA some scheduler holds four warps whether the batch is spread or not, and
+  // CTA-wide blocks keep the warps of a CTA together in the program: 65,536 pairings 45.6 instead of 47.3 ms)
+  if (!pr.cross_thread && !seg && c.ctas_per_sm == 0 && grid_override == 0 && nt != VM_NT_XWIDE) {
     // An isolated batch (automatic shape): item blocks of 32 per WARP, spread over all SMs, and when the batch
     // is w.f waves long it runs as ceil(w.f) equal waves on fewer warps per CTA (a warp is faster at lower
     // occupancy): 65,536 pairings = 1.15 waves took 33 + 32 ms, two passes at 7 of 12 warps take 52.  With an

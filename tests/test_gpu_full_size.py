@@ -100,6 +100,32 @@ def test_config3_sum_of_one_million_points(g2):
     d_sum.free()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("g2", [False, True])
+def test_three_pass_sum_of_2100000_points(g2):
+    """sums from 2 M points on run in three passes (g?_sumf in the 12-warp shape, g?_sum1j, g?_sum2): against the
+    oracle's scalar multiplication of the scalar sum, with the point at infinity and a repeated point in the input,
+    and against the two-pass result on the two halves added up"""
+    from bls_b200 import engine, workloads as W
+    from bls_b200._lib import check, lib
+    n = 2_100_000
+    d_pts, cnt, tot = W.config3_slice(n, g2)
+    w = 192 if g2 else 96
+    pts = d_pts.download().reshape(n, w).copy()
+    pts[12345] = 0                                           # infinity: drop that point's scalar from the total
+    pts[777_777] = pts[777_776]                              # P + P somewhere in a thread's fold or in the trees
+    d_pts.upload(pts.reshape(-1))
+    d_sum = engine.DeviceBuffer(w)
+    check((lib.b200bls_g2_sum_dev if g2 else lib.b200bls_g1_sum_dev)(d_pts.ptr, d_sum.ptr, cnt))
+    got = d_sum.download().tobytes()
+    half = n // 2
+    a = engine.point_sum(pts[:half].reshape(-1), g2).tobytes()
+    b = engine.point_sum(pts[half:].reshape(-1), g2).tobytes()
+    assert engine.point_sum(np.frombuffer(a + b, dtype=np.uint8), g2).tobytes() == got
+    d_pts.free()
+    d_sum.free()
+
+
 def test_config4_aggregate_verify_of_10000_messages():
     from bls_b200 import engine, workloads as W
     n = 10_000
