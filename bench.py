@@ -496,6 +496,17 @@ def run_configs(rank, world, allmax, barrier, D, W, engine, lib, check, np, synt
         ok = d_sum.download().tobytes() == W.expected_multiple(tot, g2)
         ms = allmax([ms])[0]
         c3[name] = {"ms": ms, "adds_per_s_per_gpu": (n3 - 1) / (ms * 1e-3), "parity_sum_equals_scalar_sum_times_G": bool(ok)}
+        # secure aggregation: the same points under 254-bit exponents t_i, sum_i t_i P_i as ONE multi-scalar
+        # multiplication (bls.py:29-56, 217-221 multiply every point by its exponent and fold)
+        tsc = synth.scalars(synth.SEED_AGGREGATE + 17, n3)
+        d_t = engine.DeviceBuffer(32 * n3).upload(tsc)
+        fm = lib.b200bls_g2_msm_dev if g2 else lib.b200bls_g1_msm_dev
+        check(fm(d_pts.ptr, d_t.ptr, d_sum.ptr, cnt))
+        ms_m = allmax([W.timed(lambda: check(fm(d_pts.ptr, d_t.ptr, d_sum.ptr, cnt)), reps=2)])[0]
+        dot = sum(a * b for a, b in zip(W.ints(synth.scalars(synth.SEED_AGGREGATE, n3)), W.ints(tsc))) % W.N
+        c3[name]["secure_msm"] = {"ms": ms_m, "points_per_s_per_gpu": n3 / (ms_m * 1e-3),
+                                  "parity_equals_dot_product_times_G": bool(d_sum.download().tobytes() == W.expected_multiple(dot, g2))}
+        d_t.free()
         d_pts.free()
         d_sum.free()
     out["config3_aggregate_1M"] = c3
