@@ -145,6 +145,41 @@ def test_sum_programs_with_skipped_and_executed_regions(g2):
             assert out.tobytes() == want, paired
 
 
+@pytest.mark.parametrize("g2", [False, True])
+def test_three_pass_sum_programs(g2):
+    """large sums: per-thread fold (g?_sumf, no cross-thread step, workspace partly in tensor memory), Jacobian fold +
+    CTA tree (g?_sum1j), one CTA (g?_sum2) -- incl. P + P, P + (-P), infinity, more points than threads (several
+    item blocks per thread) and fewer (threads whose partial stays the identity)"""
+    G = O.G2 if g2 else O.G1
+    w = 192 if g2 else 96
+
+    def ser(p):
+        if g2:
+            return b"".join(c.to_bytes(48, "big") for c in (p[0][0], p[0][1], p[1][0], p[1][1]))
+        return p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+    pts = [O.aff_mul(k, G) for k in (3, 5, 7, 11, 13, 17, 19)]
+    for plist, nt_a, nb_a in ((pts + [pts[1], pts[1], O.aff_neg(pts[2])] + pts[3:], 3, 2),      # 14 points + infinity on 6 threads
+                              (pts[:3], 4, 2)):                                                # 3 points + infinity on 8 threads
+        data = b"".join(ser(p) for p in plist) + bytes(w)
+        n = len(data) // w
+        want = ser((O.g2_sum if g2 else O.g1_sum)(plist))
+        af = curve.build_sum_fold(g2)().assemble(6, n_cold=4096, n_tmem=7)
+        aj = curve.build_sum_pass1j(g2)().assemble(9, n_tmem=10)
+        a2 = curve.build_sum_pass2(g2)().assemble(9, n_tmem=10)
+        elems = 3 if g2 else 2
+        parts = nt_a * nb_a
+        raw_a = np.zeros(elems * 6 * parts * 16, dtype=np.uint8)
+        hostsim.run(af, {0: np.frombuffer(data, dtype=np.uint8).copy(), 1: raw_a}, {0: w, 1: parts}, n,
+                    n_blocks=nb_a, nt=nt_a, paired=False)
+        n_parts = min(n, parts)                     # threads beyond the item count store nothing (sum_dev: n >= parts)
+        nb = 2
+        raw_b = np.zeros(elems * 6 * nb * 16, dtype=np.uint8)
+        hostsim.run(aj, {0: raw_a, 1: raw_b}, {0: parts, 1: nb}, n_parts, n_blocks=nb, nt=128, paired=False)
+        out = np.zeros(w, dtype=np.uint8)
+        hostsim.run(a2, {0: raw_b, 1: out}, {0: nb, 1: w}, nb, n_blocks=1, nt=128, paired=False)
+        assert out.tobytes() == want, (g2, len(plist))
+
+
 def test_field_programs_on_weakly_reduced_edge_values():
     """operands 0, 1, q-1 and values >= q on input (reduced on load): mul / inv / sub at level 12"""
     import random
