@@ -131,3 +131,21 @@ def test_ec_module_mirrors_untwist_twist_psi_sw_encode_and_point_classes():
         assert got.infinity == c["out"]["inf"]
         if not got.infinity:
             assert got.raw.hex() == c["out"]["x"] + c["out"]["y"]
+
+
+def test_point_scalars_outside_256_bits_follow_the_reference():
+    """AffinePoint.__mul__ / JacobianPoint.__mul__ (ec.py:61-66, 151-156) accept any Python int: scalars of 2^256 and
+    more, multiples of the group order and negative ones reach the 32-byte device ladder reduced mod n"""
+    from bls_b200 import ec
+    import bls_oracle as O
+    ks = [O.N + 5, (1 << 256) + 5, (1 << 300) + 12345, 3 * O.N, -7, O.N - 1]
+    for g2, gen, G in ((False, ec.generator_Fq(), O.G1), (True, ec.generator_Fq2(), O.G2)):
+        many = ec.scalar_mul_many([gen] * len(ks), ks, g2)
+        for k, m in zip(ks, many):
+            want = O.aff_mul(k % O.N, G)
+            if g2:
+                wb = bytes(192) if want[2] else b"".join(c.to_bytes(48, "big") for c in (want[0][0], want[0][1], want[1][0], want[1][1]))
+            else:
+                wb = bytes(96) if want[2] else want[0].to_bytes(48, "big") + want[1].to_bytes(48, "big")
+            assert m.raw == wb, (g2, k)
+            assert (gen * k).raw == wb, (g2, k)
