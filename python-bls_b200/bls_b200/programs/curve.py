@@ -413,6 +413,37 @@ def build_sum_pass1j(g2):
     return build
 
 
+def build_sum_small(g2):
+    """Small sums in ONE launch of one CTA: buffers 0 = affine points (n items), 1 = out (affine, one point).  The fold
+    of g?_sum1 followed directly by the tree and the to_affine of g?_sum2: up to a few hundred points (the 8 per-rank
+    partial sums of a sharded aggregation, the two or three signatures of an AggregationInfo merge) do not need two
+    passes."""
+    def build():
+        prog = Program("g2_sums" if g2 else "g1_sums")
+        c = Curve(prog, g2)
+        inf0 = c.infinity()
+        if g2:
+            acc = [prog.var2(v) for v in inf0]
+        else:
+            acc = [prog.var2(prog.pack(v, v)) for v in inf0]
+        prog.begin_body()
+        x, y, inf = c.load_affine(0)
+        inf = inf | ~prog.flag_active()
+        cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
+        s = c.add(cur, (x, y), mixed=True, inf2=inf)
+        for a, v in zip(acc, s):
+            if g2:
+                prog.assign(a, v)
+            else:
+                prog.emit("MOV1", a.c0, v)
+        prog.begin_epilogue()
+        cur = tuple(acc) if g2 else tuple(a.c0 for a in acc)
+        tot = _tree_reduce(prog, c, cur)
+        c.store_affine(1, 0, c.to_affine(tot), block_only=True)
+        return prog
+    return build
+
+
 def build_sum_pass2(g2):
     """buffers: 0 = raw SoA partials (n items, one per CTA of pass 1), 1 = out (affine, one
     point).  Launched with a single CTA."""

@@ -56,6 +56,7 @@ for _g2 in (False, True):
     PROGRAMS[_p + "_add"] = curve.build_add(_g2)
     PROGRAMS[_p + "_sum1"] = curve.build_sum_pass1(_g2)
     PROGRAMS[_p + "_sum2"] = curve.build_sum_pass2(_g2)
+    PROGRAMS[_p + "_sums"] = curve.build_sum_small(_g2)
     PROGRAMS[_p + "_sumf"] = curve.build_sum_fold(_g2)
     PROGRAMS[_p + "_sum1j"] = curve.build_sum_pass1j(_g2)
     PROGRAMS[_p + "_bucket"] = curve.build_bucket_fold(_g2)

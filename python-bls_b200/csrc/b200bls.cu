@@ -103,6 +103,8 @@ struct Context {
   // most of the GPU empty, the one-thread kernel otherwise.  Environment variable B200BLS_KERNEL.
   int kernel = 0;
   int isolated_shape = 0;   // experiments: B200BLS_ISOLATED_SHAPE forces the shape of automatic (isolated) launches
+  // segment tables of the serial tiny sums (sum_dev): idx[16] = 0..15, then for n = 0..16 the pair {0, n}
+  unsigned* tiny_seg = nullptr;
 };
 
 Context g_ctx;
@@ -440,6 +442,10 @@ VmBuf vb(const void* p, long long stride) {
 // From 2 M points on, three passes (below): measured 1 M G2 points 2.81 ms in two passes, 2.95 in three; 8 M points
 // 19 ms in two, 13.7 in three (the third pass costs ~0.8 ms, the 12-warp fold saves 0.7 ms per million points).
 constexpr size_t kSumThreePassMin = 2000000;
+// Up to 1,024 points (eight per thread of one CTA) in ONE launch: the second pass costs more than the serial adds it saves.
+constexpr size_t kSumOnePassMax = 1024;
+// Up to 6 points: one thread adds them one after the other (measured below that: 7 tree levels cost more).
+constexpr size_t kSumSerialMax = 6;
 int sum_dev(bool g2, const void* pts, void* out, size_t n) {
   NEED_READY();
   const char* n1 = g2 ? "g2_sum1" : "g1_sum1";
@@ -448,6 +454,17 @@ int sum_dev(bool g2, const void* pts, void* out, size_t n) {
   if (n == 0) {  // empty sum = point at infinity = zero bytes
     CU(cudaMemsetAsync(out, 0, w, STREAM));
     return 0;
+  }
+  if (n <= kSumSerialMax) {   // a handful of points: ONE thread folds them (the bucket program on one segment)
+    const DevProgram* pb = find_program(g2 ? "g2_bucket" : "g1_bucket", 1);
+    if (!pb) return B200BLS_E_PROGRAM;
+    SegArgs seg = {g_ctx.tiny_seg + 16 + 2 * n, g_ctx.tiny_seg};
+    VmBuf bs[2] = {vb(pts, (long long)w), vb(out, (long long)w)};
+    return launch_program(*pb, 1, bs, 2, 0, &seg);
+  }
+  if (n <= kSumOnePassMax) {   // one CTA, one launch: fold, tree and to_affine in the same program
+    VmBuf bs[2] = {vb(pts, (long long)w), vb(out, (long long)w)};
+    return launch_named(g2 ? "g2_sums" : "g1_sums", n, bs, 2, 1);
   }
   if (n >= kSumThreePassMin && g_ctx.kernel != 2) {
     // Large sums in three passes.  A: every thread of the 12-warp shape folds its share with mixed additions and
@@ -884,6 +901,16 @@ int b200bls_init(int device) {
   }
   CU(cudaEventCreate(&c.ev0));
   CU(cudaEventCreate(&c.ev1));
+  {
+    unsigned tab[16 + 2 * 17];
+    for (unsigned i = 0; i < 16; i++) tab[i] = i;
+    for (unsigned n = 0; n <= 16; n++) {
+      tab[16 + 2 * n] = 0;
+      tab[16 + 2 * n + 1] = n;
+    }
+    CU(cudaMalloc(&c.tiny_seg, sizeof(tab)));
+    CU(cudaMemcpy(c.tiny_seg, tab, sizeof(tab), cudaMemcpyHostToDevice));
+  }
   CU(vm1_configure());
   CU(vm2_configure());
   CU(vm3_configure());
@@ -979,6 +1006,8 @@ void b200bls_shutdown(void) {
   }
   cudaEventDestroy(c.ev0);
   cudaEventDestroy(c.ev1);
+  if (c.tiny_seg) cudaFree(c.tiny_seg);
+  c.tiny_seg = nullptr;
   c.ready = false;
   c.device = -1;
 }

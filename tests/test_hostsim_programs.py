@@ -146,6 +146,32 @@ def test_sum_programs_with_skipped_and_executed_regions(g2):
 
 
 @pytest.mark.parametrize("g2", [False, True])
+def test_one_launch_small_sum_program(g2):
+    """g?_sums: fold, CTA tree and to_affine in one program on one block -- fewer points than threads, more points
+    than threads (several item blocks), P + P, P + (-P), infinity"""
+    G = O.G2 if g2 else O.G1
+    w = 192 if g2 else 96
+
+    def ser(p):
+        if p[2]:
+            return bytes(w)
+        if g2:
+            return b"".join(c.to_bytes(48, "big") for c in (p[0][0], p[0][1], p[1][0], p[1][1]))
+        return p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+    pts = [O.aff_mul(k, G) for k in (3, 5, 7, 11, 13)]
+    asm = curve.build_sum_small(g2)().assemble(9, n_tmem=10)
+    for plist in (pts[:1], pts[:2] + [O.aff_neg(pts[1])], pts + [pts[1], pts[1], O.aff_neg(pts[2])] + pts * 30):
+        data = b"".join(ser(p) for p in plist) + bytes(w)                 # + the point at infinity
+        n = len(data) // w
+        want = ser((O.g2_sum if g2 else O.g1_sum)(plist))
+        for paired in (False, True):
+            out = np.zeros(w, dtype=np.uint8)
+            hostsim.run(asm, {0: np.frombuffer(data, dtype=np.uint8).copy(), 1: out}, {0: w, 1: w}, n, n_blocks=1, nt=128,
+                        paired=paired)
+            assert out.tobytes() == want, (g2, len(plist), paired)
+
+
+@pytest.mark.parametrize("g2", [False, True])
 def test_three_pass_sum_programs(g2):
     """large sums: per-thread fold (g?_sumf, no cross-thread step, workspace partly in tensor memory), Jacobian fold +
     CTA tree (g?_sum1j), one CTA (g?_sum2) -- incl. P + P, P + (-P), infinity, more points than threads (several
